@@ -1,0 +1,63 @@
+"""Builds libnngpara.so (hand-written sm_100a CUDA + the C ABI of include/nngpara.h) in-tree
+with nvcc.  No JIT cache: the .so sits next to this file so it travels to the GPU box."""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libnngpara.so")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
+          "-I", CSRC]
+# (source, extra flags): the RK and kNN units reproduce NumPy/SciPy rounding, so no FMA contraction
+UNITS = [("rk.cu", ["-fmad=false"]), ("knn.cu", ["-fmad=false"]), ("gpfit.cu", []), ("api.cu", [])]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libnngpara.so cannot be built")
+    return exe
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "nngpara.h")]
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        srcp = os.path.join(CSRC, src)
+        if force or _stale(obj, [srcp] + headers):
+            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose:
+            print(out)
+    if force or _stale(LIB_PATH, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB_PATH] + objs
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

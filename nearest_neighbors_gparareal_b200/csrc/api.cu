@@ -1,0 +1,545 @@
+// extern "C" entry points of libnngpara.so (see include/nngpara.h), handle management,
+// host-buffer variants, the fused on-device sweep and the roofline micro-benchmarks.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstring>
+
+static std::string g_create_error;
+
+int nngp_fail(nngp_handle_t h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return -1;
+}
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+void* nngp_workspace(nngp_handle_t h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return h->ws;
+  // grow: work already enqueued may still use the old block
+  cudaDeviceSynchronize();
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  size_t want = bytes + bytes / 4 + (1 << 20);
+  if (cudaMalloc(&h->ws, want) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  h->ws_bytes = want;
+  return h->ws;
+}
+
+static void* pinned_buf(nngp_handle_t h, size_t bytes) {
+  if (bytes <= h->pinned_bytes) return h->pinned;
+  if (h->pinned) cudaFreeHost(h->pinned);
+  h->pinned = nullptr;
+  h->pinned_bytes = 0;
+  size_t want = bytes + bytes / 4 + (1 << 16);
+  if (cudaMallocHost(&h->pinned, want) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  h->pinned_bytes = want;
+  return h->pinned;
+}
+
+static void* stage_buf(nngp_handle_t h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return h->stage;
+  cudaDeviceSynchronize();
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  size_t want = bytes + bytes / 4 + (1 << 16);
+  if (cudaMalloc(&h->stage, want) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  h->stage_bytes = want;
+  return h->stage;
+}
+
+// simple carve-out helper over a byte block (256 B aligned pieces)
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  template <class T> T* take(size_t count) {
+    T* p = (T*)(base + off);
+    off += ((count * sizeof(T) + 255) / 256) * 256;
+    return p;
+  }
+  static size_t pad(size_t bytes) { return ((bytes + 255) / 256) * 256; }
+};
+
+extern "C" {
+
+int nngp_abi_version(void) { return NNGP_ABI_VERSION; }
+
+int nngp_create(int device, nngp_handle_t* out) {
+  if (!out) return nngp_fail(nullptr, "nngp_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return nngp_fail(nullptr, "nngp_create: no CUDA device (%s); this library has no CPU fallback",
+                     cudaGetErrorString(e));
+  if (device < 0 || device >= count) return nngp_fail(nullptr, "nngp_create: device %d of %d", device, count);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return nngp_fail(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return nngp_fail(nullptr, "nngp_create: device sm_%d%d is not Blackwell sm_100a", prop.major, prop.minor);
+  nngp_handle_t h = new nngp_handle_s();
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return nngp_fail(nullptr, "cudaStreamCreate failed");
+  }
+  if (rk_set_tableaus(h) != 0) {
+    g_create_error = h->err;
+    delete h;
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+int nngp_destroy(nngp_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& s : h->systems) {
+    if (s.d_mn) cudaFree(s.d_mn);
+    if (s.d_mx) cudaFree(s.d_mx);
+  }
+  if (h->ds_x) cudaFree(h->ds_x);
+  if (h->ds_y) cudaFree(h->ds_y);
+  if (h->ds_xt) cudaFree(h->ds_xt);
+  if (h->ws) cudaFree(h->ws);
+  if (h->stage) cudaFree(h->stage);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+const char* nngp_last_error(nngp_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int nngp_synchronize(nngp_handle_t h, void* stream) {
+  NNGP_CUDA(h, cudaStreamSynchronize(as_stream(stream)));
+  return 0;
+}
+
+long long nngp_launch_count(nngp_handle_t h) { return h->launches; }
+
+// ---- systems ---------------------------------------------------------------------------
+int nngp_system_create(nngp_handle_t h, int system_id, int d, const double* params, int n_params,
+                       int normalize, const double* mn, const double* mx, int* sys_out) {
+  if (!sys_out) return nngp_fail(h, "system_create: sys_out is NULL");
+  if (system_id < NNGP_SYS_FHN_ODE || system_id > NNGP_SYS_BURGERS)
+    return nngp_fail(h, "system_create: unknown system id %d", system_id);
+  if (n_params < 0 || n_params > NNGP_MAX_PARAMS) return nngp_fail(h, "system_create: n_params=%d", n_params);
+  if (d < 1) return nngp_fail(h, "system_create: d=%d", d);
+  if (normalize != 0 && normalize != 1) return nngp_fail(h, "Only identity and -11 are implemented");
+  if (normalize && (!mn || !mx)) return nngp_fail(h, "system_create: normalize=1 needs mn and mx");
+  SystemDesc s;
+  s.system_id = system_id;
+  s.d = d;
+  s.n_params = n_params;
+  for (int i = 0; i < n_params; i++) s.params[i] = params[i];
+  s.normalize = normalize;
+  if (normalize) {
+    NNGP_CUDA(h, cudaMalloc(&s.d_mn, sizeof(double) * d));
+    NNGP_CUDA(h, cudaMalloc(&s.d_mx, sizeof(double) * d));
+    NNGP_CUDA(h, cudaMemcpy(s.d_mn, mn, sizeof(double) * d, cudaMemcpyHostToDevice));
+    NNGP_CUDA(h, cudaMemcpy(s.d_mx, mx, sizeof(double) * d, cudaMemcpyHostToDevice));
+  }
+  h->systems.push_back(s);
+  *sys_out = (int)h->systems.size() - 1;
+  return 0;
+}
+
+static int get_sys(nngp_handle_t h, int sys, const SystemDesc** out) {
+  if (sys < 0 || sys >= (int)h->systems.size()) return nngp_fail(h, "bad system handle %d", sys);
+  *out = &h->systems[sys];
+  return 0;
+}
+
+int nngp_rhs_eval(nngp_handle_t h, int sys, int n, const double* d_u, double* d_out, void* stream) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  return rhs_launch(h, *s, n, d_u, d_out, as_stream(stream));
+}
+
+int nngp_rhs_eval_host(nngp_handle_t h, int sys, int n, const double* u, double* out) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  const size_t bytes = sizeof(double) * (size_t)n * s->d;
+  double* dev = (double*)stage_buf(h, 2 * Carver::pad(bytes));
+  if (!dev) return nngp_fail(h, "rhs_eval_host: out of device memory");
+  double* dout = (double*)((char*)dev + Carver::pad(bytes));
+  NNGP_CUDA(h, cudaMemcpyAsync(dev, u, bytes, cudaMemcpyHostToDevice, h->own_stream));
+  if (int rc = rhs_launch(h, *s, n, dev, dout, h->own_stream)) return rc;
+  NNGP_CUDA(h, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, h->own_stream));
+  NNGP_CUDA(h, cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
+// ---- propagators -----------------------------------------------------------------------
+int nngp_rk_batch(nngp_handle_t h, int sys, int method, int h_mode, long long steps, int n_slices,
+                  const double* d_t0, const double* d_t1, const double* d_u0, long long ld_u0,
+                  double* d_u1, long long ld_u1, void* stream) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  return rk_launch(h, *s, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1,
+                   as_stream(stream));
+}
+
+int nngp_rk_batch_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps,
+                       int n_slices, const double* t0, const double* t1, const double* u0,
+                       double* u1) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  if (n_slices <= 0) return 0;
+  const int d = s->d;
+  const size_t nb_t = sizeof(double) * (size_t)n_slices, nb_u = nb_t * d;
+  // pinned staging: [t0 | t1 | u0] in, [u1] out
+  const size_t in_bytes = 2 * Carver::pad(nb_t) + Carver::pad(nb_u);
+  char* pin = (char*)pinned_buf(h, in_bytes + Carver::pad(nb_u));
+  char* dev = (char*)stage_buf(h, in_bytes + Carver::pad(nb_u));
+  if (!pin || !dev) return nngp_fail(h, "rk_batch_host: out of staging memory");
+  Carver cp(pin), cd(dev);
+  double* p_t0 = cp.take<double>(n_slices); double* p_t1 = cp.take<double>(n_slices);
+  double* p_u0 = cp.take<double>((size_t)n_slices * d); double* p_u1 = cp.take<double>((size_t)n_slices * d);
+  double* g_t0 = cd.take<double>(n_slices); double* g_t1 = cd.take<double>(n_slices);
+  double* g_u0 = cd.take<double>((size_t)n_slices * d); double* g_u1 = cd.take<double>((size_t)n_slices * d);
+  memcpy(p_t0, t0, nb_t);
+  memcpy(p_t1, t1, nb_t);
+  memcpy(p_u0, u0, nb_u);
+  NNGP_CUDA(h, cudaMemcpyAsync(g_t0, p_t0, in_bytes, cudaMemcpyHostToDevice, h->own_stream));
+  if (int rc = rk_launch(h, *s, method, h_mode, steps, n_slices, g_t0, g_t1, g_u0, d, g_u1, d, h->own_stream)) return rc;
+  NNGP_CUDA(h, cudaMemcpyAsync(p_u1, g_u1, nb_u, cudaMemcpyDeviceToHost, h->own_stream));
+  NNGP_CUDA(h, cudaStreamSynchronize(h->own_stream));
+  memcpy(u1, p_u1, nb_u);
+  return 0;
+}
+
+int nngp_get_tableau(int method, int* stages, double* a, double* b, double* c) {
+  if (method != 1 && method != 2 && method != 4 && method != 8) return -1;
+  rk_host_tableau(method, stages, a, b, c);
+  return 0;
+}
+
+// ---- dataset ---------------------------------------------------------------------------
+int nngp_dataset_reserve(nngp_handle_t h, long long cap_rows, int d) {
+  if (cap_rows < 1 || d < 1) return nngp_fail(h, "dataset_reserve: cap_rows=%lld d=%d", cap_rows, d);
+  if (h->ds_x && h->ds_d == d && h->ds_cap >= cap_rows) return 0;
+  if (h->ds_x && h->ds_d != d && h->ds_rows > 0)
+    return nngp_fail(h, "dataset_reserve: dimension change %d -> %d with %lld rows held", h->ds_d, d, h->ds_rows);
+  NNGP_CUDA(h, cudaDeviceSynchronize());
+  double *nx = nullptr, *ny = nullptr, *nxt = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)cap_rows * d;
+  NNGP_CUDA(h, cudaMalloc(&nx, bytes));
+  NNGP_CUDA(h, cudaMalloc(&ny, bytes));
+  NNGP_CUDA(h, cudaMalloc(&nxt, bytes));
+  const long long keep = (h->ds_x && h->ds_d == d) ? h->ds_rows : 0;
+  double *ox = h->ds_x, *oy = h->ds_y, *oxt = h->ds_xt;
+  h->ds_x = nx; h->ds_y = ny; h->ds_xt = nxt;
+  h->ds_d = d; h->ds_cap = cap_rows; h->ds_rows = 0;
+  if (keep > 0) {
+    if (int rc = dataset_append_launch(h, ox, oy, keep, nullptr)) return rc;
+    NNGP_CUDA(h, cudaDeviceSynchronize());
+  }
+  if (ox) cudaFree(ox);
+  if (oy) cudaFree(oy);
+  if (oxt) cudaFree(oxt);
+  return 0;
+}
+
+int nngp_dataset_reset(nngp_handle_t h) {
+  h->ds_rows = 0;
+  return 0;
+}
+
+long long nngp_dataset_rows(nngp_handle_t h) { return h->ds_rows; }
+int nngp_dataset_dim(nngp_handle_t h) { return h->ds_d; }
+
+int nngp_dataset_append(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
+                        void* stream) {
+  return dataset_append_launch(h, d_x, d_y, rows, as_stream(stream));
+}
+
+int nngp_dataset_append_host(nngp_handle_t h, const double* x, const double* y, long long rows) {
+  if (rows <= 0) return 0;
+  if (!h->ds_x) return nngp_fail(h, "dataset not reserved (call nngp_dataset_reserve)");
+  if (h->ds_rows + rows > h->ds_cap) {
+    long long want = h->ds_cap * 2;
+    if (want < h->ds_rows + rows) want = h->ds_rows + rows;
+    if (int rc = nngp_dataset_reserve(h, want, h->ds_d)) return rc;
+  }
+  const size_t bytes = sizeof(double) * (size_t)rows * h->ds_d;
+  char* dev = (char*)stage_buf(h, 2 * Carver::pad(bytes));
+  if (!dev) return nngp_fail(h, "dataset_append_host: out of device memory");
+  double* gx = (double*)dev;
+  double* gy = (double*)(dev + Carver::pad(bytes));
+  NNGP_CUDA(h, cudaMemcpyAsync(gx, x, bytes, cudaMemcpyHostToDevice, h->own_stream));
+  NNGP_CUDA(h, cudaMemcpyAsync(gy, y, bytes, cudaMemcpyHostToDevice, h->own_stream));
+  if (int rc = dataset_append_launch(h, gx, gy, rows, h->own_stream)) return rc;
+  NNGP_CUDA(h, cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
+int nngp_append_iteration(nngp_handle_t h, const double* d_u_cur, const double* d_uF,
+                          const double* d_uG_cur, int N, int I, int d, void* stream) {
+  return append_iteration_launch(h, d_u_cur, d_uF, d_uG_cur, N, I, d, as_stream(stream));
+}
+
+int nngp_rowwise_maxabs_diff(nngp_handle_t h, const double* d_a, const double* d_b, int rows,
+                             int d, double* d_err, void* stream) {
+  return rowwise_maxabs_launch(h, d_a, d_b, rows, d, d_err, as_stream(stream));
+}
+
+// ---- kNN -------------------------------------------------------------------------------
+int nngp_knn(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
+             long long* d_idx, double* d_dist, void* stream) {
+  const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
+  void* ws = nngp_workspace(h, knn_workspace_bytes(nq, n, m));
+  if (!ws) return nngp_fail(h, "knn: out of device memory for %d x %lld distances", nq, n);
+  return knn_launch(h, d_q, nq, m, n_rows, d_idx, d_dist, ws, as_stream(stream));
+}
+
+int nngp_knn_host(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
+                  long long* idx, double* dist) {
+  if (nq <= 0) return 0;
+  const int d = h->ds_d;
+  const size_t bq = Carver::pad(sizeof(double) * (size_t)nq * d);
+  const size_t bi = Carver::pad(sizeof(long long) * (size_t)nq * m);
+  const size_t bd = Carver::pad(sizeof(double) * (size_t)nq * m);
+  char* dev = (char*)stage_buf(h, bq + bi + bd);
+  if (!dev) return nngp_fail(h, "knn_host: out of device memory");
+  double* gq = (double*)dev;
+  long long* gi = (long long*)(dev + bq);
+  double* gd = (double*)(dev + bq + bi);
+  NNGP_CUDA(h, cudaMemcpyAsync(gq, q, sizeof(double) * (size_t)nq * d, cudaMemcpyHostToDevice, h->own_stream));
+  if (int rc = nngp_knn(h, gq, nq, m, n_rows, gi, gd, h->own_stream)) return rc;
+  NNGP_CUDA(h, cudaMemcpyAsync(idx, gi, sizeof(long long) * (size_t)nq * m, cudaMemcpyDeviceToHost, h->own_stream));
+  NNGP_CUDA(h, cudaMemcpyAsync(dist, gd, sizeof(double) * (size_t)nq * m, cudaMemcpyDeviceToHost, h->own_stream));
+  NNGP_CUDA(h, cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
+// ---- GP fit / predict ------------------------------------------------------------------
+// workspace layout for a fit on nq queries: [knn distances nq*n | r2 nq*m*m]
+static int fit_workspace(nngp_handle_t h, int nq, long long n, int m, void** knn_ws, double** r2) {
+  const size_t bk = Carver::pad(knn_workspace_bytes(nq, n, m));
+  const size_t br = Carver::pad(gp_prep_bytes(nq, m));
+  char* ws = (char*)nngp_workspace(h, bk + br);
+  if (!ws) return nngp_fail(h, "fit: out of device memory (workspace %zu bytes)", bk + br);
+  *knn_ws = ws;
+  *r2 = (double*)(ws + bk);
+  return 0;
+}
+
+int nngp_fit_predict(nngp_handle_t h, const double* d_q, const long long* d_idx,
+                     const double* d_dist, int nq, int m, int n_restarts,
+                     const signed char* d_starts, double fatol, double xatol, double* d_pred,
+                     double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt, int* d_nfev,
+                     double* d_fvals, double* d_thetas, void* stream) {
+  (void)d_q;
+  void* kws; double* r2;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
+  return gp_fit_predict_launch(h, d_idx, d_dist, r2, nq, m, n_restarts, d_starts, fatol, xatol,
+                               d_pred, nullptr, d_theta_opt, d_jitter_opt, d_fval_opt, d_nfev,
+                               d_fvals, d_thetas, st);
+}
+
+int nngp_gp_nll(nngp_handle_t h, const long long* d_idx, int nq, int m, int nt,
+                const double* d_theta, const double* d_jitter10, double* d_nll, void* stream) {
+  void* kws; double* r2;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
+  return gp_nll_launch(h, d_idx, r2, nq, m, nt, d_theta, d_jitter10, d_nll, st);
+}
+
+int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, const double* d_dist,
+                 int nq, int m, const double* d_theta, const double* d_jitter, double* d_pred,
+                 void* stream) {
+  (void)d_q;
+  void* kws; double* r2;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
+  return gp_mean_launch(h, d_idx, d_dist, r2, nq, m, d_theta, d_jitter, d_pred, st);
+}
+
+int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
+                      int n_restarts, const signed char* starts, double fatol, double xatol,
+                      double* pred, long long* idx, double* theta_opt, double* jitter_opt,
+                      double* fval_opt, int* nfev, double* fvals, double* thetas) {
+  if (nq <= 0) return 0;
+  if (!h->ds_x) return nngp_fail(h, "predict: dataset is empty");
+  const int d = h->ds_d, R = n_restarts;
+  const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
+  const size_t nqd = (size_t)nq * d, ntask = nqd * NNGP_N_JITTER * R;
+  size_t total = 0;
+  auto add = [&](size_t bytes) { size_t o = total; total += Carver::pad(bytes); return o; };
+  const size_t o_q = add(sizeof(double) * nqd), o_st = add(ntask * 2), o_idx = add(sizeof(long long) * nq * m),
+               o_dist = add(sizeof(double) * nq * m), o_pred = add(sizeof(double) * nqd),
+               o_th = add(sizeof(double) * nqd * 2), o_jit = add(sizeof(double) * nqd),
+               o_fv = add(sizeof(double) * nqd), o_nfev = add(sizeof(int) * ntask),
+               o_fvals = add(sizeof(double) * ntask), o_thetas = add(sizeof(double) * ntask * 2);
+  char* dev = (char*)stage_buf(h, total);
+  if (!dev) return nngp_fail(h, "predict_host: out of device memory (%zu bytes)", total);
+  cudaStream_t st = h->own_stream;
+  double* gq = (double*)(dev + o_q);
+  signed char* gst = (signed char*)(dev + o_st);
+  long long* gidx = (long long*)(dev + o_idx);
+  double* gdist = (double*)(dev + o_dist);
+  NNGP_CUDA(h, cudaMemcpyAsync(gq, q, sizeof(double) * nqd, cudaMemcpyHostToDevice, st));
+  NNGP_CUDA(h, cudaMemcpyAsync(gst, starts, ntask * 2, cudaMemcpyHostToDevice, st));
+  void* kws; double* r2;
+  if (int rc = fit_workspace(h, nq, n, m, &kws, &r2)) return rc;
+  if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
+  if (int rc = gp_prep_launch(h, gidx, nq, m, r2, st)) return rc;
+  if (int rc = gp_fit_predict_launch(h, gidx, gdist, r2, nq, m, R, gst, fatol, xatol,
+                                     (double*)(dev + o_pred), nullptr,
+                                     theta_opt ? (double*)(dev + o_th) : nullptr,
+                                     jitter_opt ? (double*)(dev + o_jit) : nullptr,
+                                     fval_opt ? (double*)(dev + o_fv) : nullptr,
+                                     nfev ? (int*)(dev + o_nfev) : nullptr,
+                                     fvals ? (double*)(dev + o_fvals) : nullptr,
+                                     thetas ? (double*)(dev + o_thetas) : nullptr, st))
+    return rc;
+  NNGP_CUDA(h, cudaMemcpyAsync(pred, dev + o_pred, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));
+  if (idx) NNGP_CUDA(h, cudaMemcpyAsync(idx, gidx, sizeof(long long) * nq * m, cudaMemcpyDeviceToHost, st));
+  if (theta_opt) NNGP_CUDA(h, cudaMemcpyAsync(theta_opt, dev + o_th, sizeof(double) * nqd * 2, cudaMemcpyDeviceToHost, st));
+  if (jitter_opt) NNGP_CUDA(h, cudaMemcpyAsync(jitter_opt, dev + o_jit, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));
+  if (fval_opt) NNGP_CUDA(h, cudaMemcpyAsync(fval_opt, dev + o_fv, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));
+  if (nfev) NNGP_CUDA(h, cudaMemcpyAsync(nfev, dev + o_nfev, sizeof(int) * ntask, cudaMemcpyDeviceToHost, st));
+  if (fvals) NNGP_CUDA(h, cudaMemcpyAsync(fvals, dev + o_fvals, sizeof(double) * ntask, cudaMemcpyDeviceToHost, st));
+  if (thetas) NNGP_CUDA(h, cudaMemcpyAsync(thetas, dev + o_thetas, sizeof(double) * ntask * 2, cudaMemcpyDeviceToHost, st));
+  NNGP_CUDA(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- fused on-device sweep (parareal.py:359-382) --------------------------------------
+int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long steps_g,
+               const double* d_t, int N, int I, int m, int n_restarts,
+               const signed char* d_starts, double fatol, double xatol, double* d_u_next,
+               double* d_uG_next, int d, void* stream) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  if (d != s->d || d != h->ds_d) return nngp_fail(h, "sweep: d=%d, system d=%d, dataset d=%d", d, s->d, h->ds_d);
+  if (I < 0 || I > N) return nngp_fail(h, "sweep: I=%d outside [0,%d]", I, N);
+  cudaStream_t st = as_stream(stream);
+  const long long n = h->ds_rows;
+  void* kws; double* r2;
+  const size_t extra = Carver::pad(sizeof(long long) * m) + Carver::pad(sizeof(double) * m);
+  {
+    const size_t bk = Carver::pad(knn_workspace_bytes(1, n, m));
+    const size_t br = Carver::pad(gp_prep_bytes(1, m));
+    char* ws = (char*)nngp_workspace(h, bk + br + extra);
+    if (!ws) return nngp_fail(h, "sweep: out of device memory");
+    kws = ws;
+    r2 = (double*)(ws + bk);
+    long long* idx = (long long*)(ws + bk + br);
+    double* dist = (double*)(ws + bk + br + Carver::pad(sizeof(long long) * m));
+    const size_t per_predict = (size_t)d * NNGP_N_JITTER * n_restarts * 2;
+    for (int i = I; i < N; i++) {
+      double* ui = d_u_next + (long long)i * d;
+      double* un = d_u_next + (long long)(i + 1) * d;
+      double* gn = d_uG_next + (long long)(i + 1) * d;
+      if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
+      if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
+      if (int rc = gp_prep_launch(h, idx, 1, m, r2, st)) return rc;
+      if (int rc = gp_fit_predict_launch(h, idx, dist, r2, 1, m, n_restarts,
+                                         d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn,
+                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st))
+        return rc;
+    }
+  }
+  return 0;
+}
+
+// ---- roofline micro-benchmarks ---------------------------------------------------------
+__global__ void fp64_fma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+int nngp_bench_fp64(nngp_handle_t h, int iters, double* tflops_out) {
+  const int blocks = 148 * 8, threads = 256;
+  double* out = (double*)nngp_workspace(h, sizeof(double) * blocks * threads);
+  if (!out) return nngp_fail(h, "bench_fp64: out of memory");
+  cudaEvent_t e0, e1;
+  NNGP_CUDA(h, cudaEventCreate(&e0));
+  NNGP_CUDA(h, cudaEventCreate(&e1));
+  fp64_fma_kernel<<<blocks, threads, 0, h->own_stream>>>(out, iters, 0.999999, 1e-7);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    NNGP_CUDA(h, cudaEventRecord(e0, h->own_stream));
+    fp64_fma_kernel<<<blocks, threads, 0, h->own_stream>>>(out, iters, 0.999999, 1e-7);
+    NNGP_CUDA(h, cudaEventRecord(e1, h->own_stream));
+    NNGP_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  h->launches += 6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
+  return 0;
+}
+
+__global__ void copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+int nngp_bench_copy(nngp_handle_t h, long long bytes, double* gbs_out) {
+  const size_t n = (size_t)bytes / sizeof(double2);
+  char* ws = (char*)nngp_workspace(h, 2 * n * sizeof(double2));
+  if (!ws) return nngp_fail(h, "bench_copy: out of memory");
+  double2* a = (double2*)ws;
+  double2* b = a + n;
+  NNGP_CUDA(h, cudaMemsetAsync(a, 0, n * sizeof(double2), h->own_stream));
+  cudaEvent_t e0, e1;
+  NNGP_CUDA(h, cudaEventCreate(&e0));
+  NNGP_CUDA(h, cudaEventCreate(&e1));
+  copy_kernel<<<148 * 16, 512, 0, h->own_stream>>>(a, b, n);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    NNGP_CUDA(h, cudaEventRecord(e0, h->own_stream));
+    copy_kernel<<<148 * 16, 512, 0, h->own_stream>>>(a, b, n);
+    NNGP_CUDA(h, cudaEventRecord(e1, h->own_stream));
+    NNGP_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double gbs = 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9;
+    if (gbs > best) best = gbs;
+  }
+  h->launches += 6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gbs_out = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Internal declarations shared by the translation units of libnngpara.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "nngpara.h"
+
+#define NNGP_MAX_PARAMS 8
+#define NNGP_MAX_STAGES 11
+
+struct SystemDesc {
+  int system_id = -1;
+  int d = 0;
+  int n_params = 0;
+  double params[NNGP_MAX_PARAMS] = {0};
+  int normalize = 0;
+  double* d_mn = nullptr;  // device [d]
+  double* d_mx = nullptr;  // device [d]
+};
+
+// Passed by value to kernels.
+struct SysArgs {
+  int system_id;
+  int d;
+  int normalize;
+  double p[NNGP_MAX_PARAMS];
+  const double* mn;
+  const double* mx;
+};
+
+struct nngp_handle_s {
+  int device = 0;
+  std::string err;
+  std::vector<SystemDesc> systems;
+  long long launches = 0;
+  // dataset (parareal.py:336-339): X,Y row-major [cap,d]; XT column-major copy [d,cap]
+  int ds_d = 0;
+  long long ds_cap = 0;
+  long long ds_rows = 0;
+  double* ds_x = nullptr;
+  double* ds_y = nullptr;
+  double* ds_xt = nullptr;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* stage = nullptr;  // device staging for *_host variants
+  size_t stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+int nngp_fail(nngp_handle_t h, const char* fmt, ...);
+#define NNGP_CUDA(h, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return nngp_fail(h, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+void* nngp_workspace(nngp_handle_t h, size_t bytes);  // grows, nullptr on failure
+SysArgs nngp_sys_args(const SystemDesc& s);
+
+// rk.cu
+int rk_set_tableaus(nngp_handle_t h);
+int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long long steps,
+              int n_slices, const double* d_t0, const double* d_t1, const double* d_u0,
+              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st);
+int rhs_launch(nngp_handle_t h, const SystemDesc& s, int n, const double* d_u, double* d_out,
+               cudaStream_t st);
+void rk_host_tableau(int method, int* S, double* a, double* b, double* c);
+
+// knn.cu
+size_t knn_workspace_bytes(int nq, long long n, int m);
+int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
+               long long* d_idx, double* d_dist, void* ws, cudaStream_t st);
+int dataset_append_launch(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
+                          cudaStream_t st);
+int append_iteration_launch(nngp_handle_t h, const double* d_u_cur, const double* d_uF,
+                            const double* d_uG_cur, int N, int I, int d, cudaStream_t st);
+int rowwise_maxabs_launch(nngp_handle_t h, const double* a, const double* b, int rows, int d,
+                          double* err, cudaStream_t st);
+
+// gpfit.cu
+size_t gp_prep_bytes(int nq, int m);
+int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, double* d_r2,
+                   cudaStream_t st);
+int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist,
+                          const double* d_r2, int nq, int m, int R, const signed char* d_starts,
+                          double fatol, double xatol, double* d_pred, const double* d_add,
+                          double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt,
+                          int* d_nfev, double* d_fvals, double* d_thetas, cudaStream_t st);
+int gp_nll_launch(nngp_handle_t h, const long long* d_idx, const double* d_r2, int nq, int m,
+                  int nt, const double* d_theta, const double* d_jitter10, double* d_nll,
+                  cudaStream_t st);
+int gp_mean_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist,
+                   const double* d_r2, int nq, int m, const double* d_theta,
+                   const double* d_jitter, double* d_pred, cudaStream_t st);
+
+// bench kernels (api.cu)

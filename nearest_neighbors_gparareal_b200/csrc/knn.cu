@@ -1,0 +1,279 @@
+// Dataset maintenance and exact FP64 nearest-neighbour search.
+//
+// Replaces  s_idx = np.argsort(cdist(new_x, self.x, 'sqeuclidean')[0,:]); s_idx[:nn]
+// (models.py:177-179) and the dataset growth x = vstack(x, ...), D = vstack(D, ...)
+// (parareal.py:336-339).
+//
+// Arithmetic contract (compiled with -fmad=false): a squared distance is the strict
+// left-to-right sum s = ((0 + (q_0-x_0)^2) + (q_1-x_1)^2) + ... with separately rounded
+// subtract, multiply and add -- SciPy's cdist arithmetic -- so the distances, and therefore
+// the index sets, are bit-exact.  Neighbours are ordered by (distance, index), i.e.
+// argsort(kind='stable').
+//
+// Layout: the dataset is kept twice, row-major X[cap,d] (row gathers for the GP) and
+// transposed XT[d,cap] so that a warp scanning 32 consecutive rows reads 32 consecutive
+// doubles per coordinate.  One thread owns one row (times TQ queries); selection keeps a
+// sorted top-m list spread over the lanes of a warp (lane l = l-th smallest) and inserts
+// with ballot + shuffle; the per-warp lists of a CTA are merged by ranking in shared memory.
+#include "common.cuh"
+
+#include <cfloat>
+
+static constexpr int KNN_SEL_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------
+// dataset append: X, Y row-major; XT transposed through a 32x32 shared-memory tile
+// ---------------------------------------------------------------------------------------
+__global__ void append_kernel(const double* __restrict__ xs, long long ldx,
+                              const double* __restrict__ ya, const double* __restrict__ yb,
+                              long long ldy, long long rows, int d, long long n0, long long cap,
+                              double* __restrict__ X, double* __restrict__ Y,
+                              double* __restrict__ XT) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.y * 32;
+  const int j0 = blockIdx.x * 32;
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const long long r = r0 + rr;
+    const int j = j0 + threadIdx.x;
+    if (r < rows && j < d) {
+      const double xv = xs[r * ldx + j];
+      X[(n0 + r) * d + j] = xv;
+      tile[rr][threadIdx.x] = xv;
+      double yv = ya[r * ldy + j];
+      if (yb != nullptr) yv = yv - yb[r * ldy + j];
+      Y[(n0 + r) * d + j] = yv;
+    }
+  }
+  __syncthreads();
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int j = j0 + jj;
+    const long long r = r0 + threadIdx.x;
+    if (r < rows && j < d) XT[(long long)j * cap + n0 + r] = tile[threadIdx.x][jj];
+  }
+}
+
+static int append_common(nngp_handle_t h, const double* xs, long long ldx, const double* ya,
+                         const double* yb, long long ldy, long long rows, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (h->ds_x == nullptr) return nngp_fail(h, "dataset not reserved (call nngp_dataset_reserve)");
+  if (h->ds_rows + rows > h->ds_cap)
+    return nngp_fail(h, "dataset capacity exceeded: %lld + %lld > %lld", h->ds_rows, rows, h->ds_cap);
+  const int d = h->ds_d;
+  dim3 block(32, 8);
+  dim3 grid((d + 31) / 32, (unsigned)((rows + 31) / 32));
+  append_kernel<<<grid, block, 0, st>>>(xs, ldx, ya, yb, ldy, rows, d, h->ds_rows, h->ds_cap,
+                                        h->ds_x, h->ds_y, h->ds_xt);
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  h->ds_rows += rows;
+  return 0;
+}
+
+int dataset_append_launch(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
+                          cudaStream_t st) {
+  return append_common(h, d_x, h->ds_d, d_y, nullptr, h->ds_d, rows, st);
+}
+
+// parareal.py:336-339: x rows u_cur[I-1 .. N-1], D rows uF[I .. N] - uG_cur[I .. N]
+int append_iteration_launch(nngp_handle_t h, const double* d_u_cur, const double* d_uF,
+                            const double* d_uG_cur, int N, int I, int d, cudaStream_t st) {
+  if (d != h->ds_d) return nngp_fail(h, "append_iteration: d=%d but dataset d=%d", d, h->ds_d);
+  if (I < 1 || I > N) return nngp_fail(h, "append_iteration: I=%d outside [1,%d]", I, N);
+  const long long rows = (long long)N - I + 1;
+  return append_common(h, d_u_cur + (long long)(I - 1) * d, d, d_uF + (long long)I * d,
+                       d_uG_cur + (long long)I * d, d, rows, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// parareal.py:402  err[p] = ||a[p,:] - b[p,:]||_inf   (one warp per row)
+// ---------------------------------------------------------------------------------------
+__global__ void rowwise_maxabs_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                      int rows, int d, double* __restrict__ err) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  double mx = 0.0;
+  bool nan = false;
+  for (int j = lane; j < d; j += 32) {
+    const double v = fabs(a[(long long)row * d + j] - b[(long long)row * d + j]);
+    nan |= (v != v);
+    mx = fmax(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan |= __shfl_xor_sync(0xffffffffu, (int)nan, o) != 0;
+  }
+  if (lane == 0) err[row] = nan ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+}
+
+int rowwise_maxabs_launch(nngp_handle_t h, const double* a, const double* b, int rows, int d,
+                          double* err, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const int wpb = 8;
+  rowwise_maxabs_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, b, rows, d, err);
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// distances: thread = one dataset row x TQ queries
+// ---------------------------------------------------------------------------------------
+template <int TQ>
+__global__ void __launch_bounds__(128)
+sqdist_kernel(const double* __restrict__ XT, long long cap, long long n, int d,
+              const double* __restrict__ Q, int nq, double* __restrict__ dist) {
+  extern __shared__ double qs[];  // [TQ][d]
+  const int q0 = blockIdx.y * TQ;
+  for (int e = threadIdx.x; e < TQ * d; e += blockDim.x) {
+    const int t = e / d, j = e - t * d;
+    qs[e] = (q0 + t < nq) ? Q[(long long)(q0 + t) * d + j] : 0.0;
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc[TQ];
+#pragma unroll
+  for (int t = 0; t < TQ; t++) acc[t] = 0.0;
+  const double* xp = XT + i;
+#pragma unroll 4
+  for (int j = 0; j < d; j++) {
+    const double x = xp[(long long)j * cap];
+#pragma unroll
+    for (int t = 0; t < TQ; t++) {
+      const double diff = qs[t * d + j] - x;
+      acc[t] = acc[t] + diff * diff;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TQ; t++)
+    if (q0 + t < nq) dist[(long long)(q0 + t) * n + i] = acc[t];
+}
+
+// query coordinates straight from global memory (any d)
+__global__ void __launch_bounds__(128)
+sqdist_kernel_gq(const double* __restrict__ XT, long long cap, long long n, int d,
+                 const double* __restrict__ Q, double* __restrict__ dist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* q = Q + (long long)blockIdx.y * d;
+  double acc = 0.0;
+  for (int j = 0; j < d; j++) {
+    const double diff = __ldg(q + j) - XT[(long long)j * cap + i];
+    acc = acc + diff * diff;
+  }
+  dist[(long long)blockIdx.y * n + i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// selection: total order (isnan, distance, index)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_less(double d1, long long i1, double d2, long long i2) {
+  const bool n1 = d1 != d1, n2 = d2 != d2;
+  if (n1 != n2) return n2;
+  if (!n1 && d1 != d2) return d1 < d2;
+  return i1 < i2;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+__global__ void __launch_bounds__(KNN_SEL_THREADS)
+select_kernel(const double* __restrict__ dist, long long n, int m, long long* __restrict__ idx_out,
+              double* __restrict__ dist_out) {
+  constexpr int NW = KNN_SEL_THREADS / 32;
+  __shared__ double cd[NW * 32];
+  __shared__ long long ci[NW * 32];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double* dq = dist + (long long)q * n;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const long long IMAX = 0x7fffffffffffffffLL;
+  // lane l holds the l-th smallest key seen by this warp (l < m)
+  double bd = INF;
+  long long bi = IMAX;
+  for (long long base = (long long)w * 32; base < n; base += KNN_SEL_THREADS) {
+    const long long i = base + lane;
+    double c = INF;
+    long long cidx = IMAX;
+    if (i < n) {
+      c = dq[i];
+      cidx = i;
+    }
+    const double td = shfl_d(bd, m - 1);
+    const long long ti = shfl_ll(bi, m - 1);
+    unsigned pending = __ballot_sync(0xffffffffu, (i < n) && key_less(c, cidx, td, ti));
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const double xd = shfl_d(c, src);
+      const long long xi = shfl_ll(cidx, src);
+      const unsigned below = __ballot_sync(0xffffffffu, (lane < m) && key_less(bd, bi, xd, xi));
+      const int pos = __popc(below);
+      const double ud = __shfl_up_sync(0xffffffffu, bd, 1);
+      const long long ui = __shfl_up_sync(0xffffffffu, bi, 1);
+      if (pos < m) {
+        if (lane > pos) {
+          bd = ud;
+          bi = ui;
+        } else if (lane == pos) {
+          bd = xd;
+          bi = xi;
+        }
+      }
+    }
+  }
+  cd[w * 32 + lane] = (lane < m) ? bd : INF;
+  ci[w * 32 + lane] = (lane < m) ? bi : IMAX;
+  __syncthreads();
+  // merge by ranking: all real keys are distinct (unique index), so ranks are unique
+  const double md = cd[threadIdx.x];
+  const long long mi = ci[threadIdx.x];
+  if (mi != IMAX) {
+    int rank = 0;
+    for (int t = 0; t < NW * 32; t++) rank += key_less(cd[t], ci[t], md, mi) ? 1 : 0;
+    if (rank < m) {
+      idx_out[(long long)q * m + rank] = mi;
+      dist_out[(long long)q * m + rank] = md;
+    }
+  }
+}
+
+size_t knn_workspace_bytes(int nq, long long n, int m) {
+  (void)m;
+  return sizeof(double) * (size_t)nq * (size_t)n;
+}
+
+int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
+               long long* d_idx, double* d_dist, void* ws, cudaStream_t st) {
+  const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
+  if (nq <= 0) return 0;
+  if (m < 1 || m > NNGP_MAX_NEIGHBOURS)
+    return nngp_fail(h, "knn: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS);
+  if (n > h->ds_rows) return nngp_fail(h, "knn: n_rows=%lld > dataset rows %lld", n, h->ds_rows);
+  if (n < m) return nngp_fail(h, "knn: dataset has %lld rows, fewer than m=%d", n, m);
+  const int d = h->ds_d;
+  double* dist = (double*)ws;
+  const int tb = 128;
+  const unsigned gx = (unsigned)((n + tb - 1) / tb);
+  const size_t qrow = (size_t)d * sizeof(double), lim = 48 * 1024;
+  if (nq >= 8 && 8 * qrow <= lim) {
+    sqdist_kernel<8><<<dim3(gx, (nq + 7) / 8), tb, 8 * qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, nq, dist);
+  } else if (nq >= 4 && 4 * qrow <= lim) {
+    sqdist_kernel<4><<<dim3(gx, (nq + 3) / 4), tb, 4 * qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, nq, dist);
+  } else if (qrow <= lim) {
+    sqdist_kernel<1><<<dim3(gx, nq), tb, qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, nq, dist);
+  } else {
+    sqdist_kernel_gq<<<dim3(gx, nq), tb, 0, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, dist);
+  }
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  select_kernel<<<nq, KNN_SEL_THREADS, 0, st>>>(dist, n, m, d_idx, d_dist);
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,619 @@
+// Batched explicit Runge-Kutta propagators and the vector fields of the named systems.
+//
+// Replaces, for all N time slices in one launch, the reference's per-slice task
+//   SolverRK.run_F / run_G -> RK.run_get_last -> _RK_numpy_   (solver.py:86-107, RK.py:101-137)
+// and the vector fields ODE.get_vector_field() (systems.py:32-44) with the Normalize affine
+// map (utils.py:14-33) fused into the right-hand side.
+//
+// Arithmetic contract: this file is compiled with -fmad=false and mirrors the reference's
+// NumPy operation order (k_i = h*f(u + sum_j a_ij k_j) accumulated left to right from 0,
+// u += np.sum(b*k) in NumPy's 8-lane pairwise order), so the closed-form ODE systems
+// reproduce the NumPy path bit for bit.  The PDE systems use the 3/5-point periodic stencil
+// form of the reference's dense difference matrices; only the order of that 3/5-term sum
+// differs from the BLAS mat-vec (ulp-level).
+//
+// Layouts: small ODEs (d<=4) one THREAD per slice, everything in registers.  PDE systems one
+// CTA per slice, one thread per grid point, the stage input staged in (double-buffered)
+// shared memory for the neighbour exchange, the k stages in registers, one barrier per stage.
+#include "common.cuh"
+
+#include <cmath>
+
+struct Tableau {
+  int S;
+  double a[NNGP_MAX_STAGES * NNGP_MAX_STAGES];
+  double b[NNGP_MAX_STAGES];
+  double c[NNGP_MAX_STAGES];
+};
+
+__constant__ Tableau c_tab[4];
+
+static int method_slot(int method) {
+  switch (method) {
+    case 1: return 0;
+    case 2: return 1;
+    case 4: return 2;
+    case 8: return 3;
+    default: return -1;
+  }
+}
+
+// RK.py:30-48, same expressions evaluated in IEEE double.
+static void build_tableau(int method, Tableau* T) {
+  for (double& v : T->a) v = 0.0;
+  for (double& v : T->b) v = 0.0;
+  for (double& v : T->c) v = 0.0;
+  auto A = [&](int i, int j) -> double& { return T->a[i * NNGP_MAX_STAGES + j]; };
+  if (method == 1) {
+    T->S = 1;
+    T->b[0] = 1.0;
+  } else if (method == 2) {
+    T->S = 2;
+    A(1, 0) = 0.5;
+    T->b[1] = 1.0;
+    T->c[1] = 0.5;
+  } else if (method == 4) {
+    T->S = 4;
+    A(1, 0) = 0.5;
+    A(2, 1) = 0.5;
+    A(3, 2) = 1.0;
+    T->b[0] = 1.0 / 6;
+    T->b[1] = 1.0 / 3;
+    T->b[2] = 1.0 / 3;
+    T->b[3] = 1.0 / 6;
+    T->c[1] = 0.5;
+    T->c[2] = 0.5;
+    T->c[3] = 1.0;
+  } else {
+    T->S = 11;
+    volatile double s21 = 21.0;
+    const double s = std::sqrt(s21);
+    A(1, 0) = 1.0 / 2;
+    A(2, 0) = 1.0 / 4;
+    A(2, 1) = 1.0 / 4;
+    A(3, 0) = 1.0 / 7;
+    A(3, 1) = (-7 - 3 * s) / 98;
+    A(3, 2) = (21 + 5 * s) / 49;
+    A(4, 0) = (11 + s) / 84;
+    A(4, 2) = (18 + 4 * s) / 63;
+    A(4, 3) = (21 - s) / 252;
+    A(5, 0) = (5 + s) / 48;
+    A(5, 2) = (9 + s) / 36;
+    A(5, 3) = (-231 + 14 * s) / 360;
+    A(5, 4) = (63 - 7 * s) / 80;
+    A(6, 0) = (10 - s) / 42;
+    A(6, 2) = (-432 + 92 * s) / 315;
+    A(6, 3) = (633 - 145 * s) / 90;
+    A(6, 4) = (-504 + 115 * s) / 70;
+    A(6, 5) = (63 - 13 * s) / 35;
+    A(7, 0) = 1.0 / 14;
+    A(7, 4) = (14 - 3 * s) / 126;
+    A(7, 5) = (13 - 3 * s) / 63;
+    A(7, 6) = 1.0 / 9;
+    A(8, 0) = 1.0 / 32;
+    A(8, 4) = (91 - 21 * s) / 576;
+    A(8, 5) = 11.0 / 72;
+    A(8, 6) = (-385 - 75 * s) / 1152;
+    A(8, 7) = (63 + 13 * s) / 128;
+    A(9, 0) = 1.0 / 14;
+    A(9, 4) = 1.0 / 9;
+    A(9, 5) = (-733 - 147 * s) / 2205;
+    A(9, 6) = (515 + 111 * s) / 504;
+    A(9, 7) = (-51 - 11 * s) / 56;
+    A(9, 8) = (132 + 28 * s) / 245;
+    A(10, 4) = (-42 + 7 * s) / 18;
+    A(10, 5) = (-18 + 28 * s) / 45;
+    A(10, 6) = (-273 - 53 * s) / 72;
+    A(10, 7) = (301 + 53 * s) / 72;
+    A(10, 8) = (28 - 28 * s) / 45;
+    A(10, 9) = (49 - 7 * s) / 18;
+    T->b[0] = 1.0 / 20;
+    T->b[7] = 49.0 / 180;
+    T->b[8] = 16.0 / 45;
+    T->b[9] = 49.0 / 180;
+    T->b[10] = 1.0 / 20;
+    const double cp = (7 + s) / 14, cm = (7 - s) / 14;
+    const double cc[11] = {0, 1.0 / 2, 1.0 / 2, cp, cp, 1.0 / 2, cm, cm, 1.0 / 2, cp, 1};
+    for (int i = 0; i < 11; i++) T->c[i] = cc[i];
+  }
+}
+
+void rk_host_tableau(int method, int* S, double* a, double* b, double* c) {
+  Tableau T;
+  build_tableau(method, &T);
+  *S = T.S;
+  for (int i = 0; i < T.S; i++) {
+    for (int j = 0; j < T.S; j++) a[i * T.S + j] = T.a[i * NNGP_MAX_STAGES + j];
+    b[i] = T.b[i];
+    c[i] = T.c[i];
+  }
+}
+
+int rk_set_tableaus(nngp_handle_t h) {
+  Tableau T[4];
+  const int methods[4] = {1, 2, 4, 8};
+  for (int i = 0; i < 4; i++) build_tableau(methods[i], &T[i]);
+  NNGP_CUDA(h, cudaMemcpyToSymbol(c_tab, T, sizeof(T)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+// x**3 as NumPy computes it (libm pow, correctly rounded in practice): product with the
+// rounding error of x*x carried along.
+__device__ __forceinline__ double cube_cr(double x) {
+  const double p = x * x;
+  const double e = fma(x, x, -p);
+  const double r = p * x;
+  const double re = fma(p, x, -r);
+  return r + (re + e * x);
+}
+
+// node time of np.linspace(t0, t1, steps+1)[n]  (RK.py:93)
+__device__ __forceinline__ double linspace_node(double t0, double t1, double step, long long n,
+                                                long long steps) {
+  return (n == steps) ? t1 : ((double)n * step + t0);
+}
+
+__device__ __forceinline__ double step_size(int h_mode, double t0, double t1, double step,
+                                            long long n, long long steps) {
+  if (h_mode == NNGP_H_CONST) return step;
+  return linspace_node(t0, t1, step, n + 1, steps) - linspace_node(t0, t1, step, n, steps);
+}
+
+// np.sum(b*k, axis=1) over S stage terms: NumPy's pairwise_sum (8 lanes, then the tail)
+template <int S>
+__device__ __forceinline__ double numpy_sum_bk(const double (&k)[S], const double* b) {
+  if constexpr (S < 8) {
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < S; i++) r = r + b[i] * k[i];
+    return r;
+  } else {
+    double r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = b[i] * k[i];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = 8; i < S; i++) res = res + b[i] * k[i];
+    return res;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// closed-form ODE systems (systems.py:80-288), evaluated on de-normalised v[D]
+// ---------------------------------------------------------------------------------------
+template <int SYS>
+struct SmallDim;
+template <> struct SmallDim<NNGP_SYS_FHN_ODE> { static constexpr int D = 2; };
+template <> struct SmallDim<NNGP_SYS_ROSSLER> { static constexpr int D = 3; };
+template <> struct SmallDim<NNGP_SYS_HOPF> { static constexpr int D = 3; };
+template <> struct SmallDim<NNGP_SYS_DBLPEND> { static constexpr int D = 4; };
+template <> struct SmallDim<NNGP_SYS_BRUSSELATOR> { static constexpr int D = 2; };
+template <> struct SmallDim<NNGP_SYS_LORENZ> { static constexpr int D = 3; };
+template <> struct SmallDim<NNGP_SYS_THOMAS> { static constexpr int D = 3; };
+
+template <int SYS, int D>
+__device__ __forceinline__ void small_field(const double* P, const double (&u)[D], double (&o)[D]) {
+  if constexpr (SYS == NNGP_SYS_FHN_ODE) {  // systems.py:97-106
+    const double a = 0.2, b = 0.2, c = 3.0;
+    o[0] = c * ((u[0] - (cube_cr(u[0]) / 3.0)) + u[1]);
+    o[1] = (-(1.0 / c)) * ((u[0] - a) + b * u[1]);
+  } else if constexpr (SYS == NNGP_SYS_ROSSLER) {  // systems.py:128-137
+    const double a = 0.2, b = 0.2, c = 5.7;
+    o[0] = (-u[1]) - u[2];
+    o[1] = u[0] + (a * u[1]);
+    o[2] = b + u[2] * (u[0] - c);
+  } else if constexpr (SYS == NNGP_SYS_HOPF) {  // systems.py:157-163, P[0] = maxtime
+    const double g = ((u[2] / P[0]) - u[0] * u[0]) - u[1] * u[1];
+    o[0] = (-u[1]) + u[0] * g;
+    o[1] = u[0] + u[1] * g;
+    o[2] = 1.0;
+  } else if constexpr (SYS == NNGP_SYS_DBLPEND) {  // systems.py:191-199
+    const double dl = u[0] - u[2];
+    const double cd = cos(dl), sd = sin(dl);
+    const double pre = -1.0 / (2.0 - cd * cd);
+    o[0] = u[1];
+    o[1] = pre * (((((u[1] * u[1]) * cd) * sd + (u[3] * u[3]) * sd) + 2.0 * sin(u[0])) - cd * sin(u[2]));
+    o[2] = u[3];
+    o[3] = pre * (((((-2.0 * (u[1] * u[1])) * sd) - ((u[3] * u[3]) * sd) * cd) - (2.0 * cd) * sin(u[0])) + 2.0 * sin(u[2]));
+  } else if constexpr (SYS == NNGP_SYS_BRUSSELATOR) {  // systems.py:217-222
+    o[0] = (1.0 + (u[0] * u[0]) * u[1]) - 4.0 * u[0];
+    o[1] = 3.0 * u[0] - (u[0] * u[0]) * u[1];
+  } else if constexpr (SYS == NNGP_SYS_LORENZ) {  // systems.py:241-247
+    o[0] = 10.0 * (u[1] - u[0]);
+    o[1] = (28.0 * u[0] - u[1]) - u[0] * u[2];
+    o[2] = u[0] * u[1] - (8.0 / 3.0) * u[2];
+  } else {  // NNGP_SYS_THOMAS, systems.py:273-288
+    const double a = 0.5, b = 10.0;
+    o[0] = (-a) * u[0] + b * sin(u[1]);
+    o[1] = (-a) * u[1] + b * sin(u[2]);
+    o[2] = (-a) * u[2] + b * sin(u[0]);
+  }
+}
+
+// normalised field systems.py:36-40: f(inverse(u)) * scale
+template <int SYS, int D>
+__device__ __forceinline__ void small_field_n(const SysArgs& A, const double (&mn)[D],
+                                              const double (&rg)[D], const double (&sc)[D],
+                                              const double (&u)[D], double (&o)[D]) {
+  if (A.normalize) {
+    double v[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) v[i] = ((u[i] + 1.0) / 2.0) * rg[i] + mn[i];
+    small_field<SYS, D>(A.p, v, o);
+#pragma unroll
+    for (int i = 0; i < D; i++) o[i] = o[i] * sc[i];
+  } else {
+    small_field<SYS, D>(A.p, u, o);
+  }
+}
+
+template <int S>
+struct SlotOf { static constexpr int value = (S == 1) ? 0 : (S == 2) ? 1 : (S == 4) ? 2 : 3; };
+
+template <int SYS, int S>
+__global__ void __launch_bounds__(32)
+rk_small_kernel(SysArgs A, int h_mode, long long steps, int n_slices,
+                const double* __restrict__ t0s, const double* __restrict__ t1s,
+                const double* __restrict__ u0, long long ld0, double* __restrict__ u1,
+                long long ld1) {
+  constexpr int D = SmallDim<SYS>::D;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slices) return;
+  const Tableau& T = c_tab[SlotOf<S>::value];
+  double mn[D], rg[D], sc[D], u[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    mn[i] = A.normalize ? A.mn[i] : 0.0;
+    rg[i] = A.normalize ? (A.mx[i] - A.mn[i]) : 2.0;
+    sc[i] = 2.0 / rg[i];
+    u[i] = u0[s * ld0 + i];
+  }
+  const double t0 = t0s[s], t1 = t1s[s];
+  const double step = (t1 - t0) / (double)steps;
+  double k[D][S];
+  for (long long n = 0; n < steps; n++) {
+    const double h = step_size(h_mode, t0, t1, step, n, steps);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      double w[D], f[D];
+#pragma unroll
+      for (int c = 0; c < D; c++) {
+        double tmp = 0.0;
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+          const double aij = T.a[i * NNGP_MAX_STAGES + j];
+          if (aij != 0.0) tmp = tmp + aij * k[c][j];
+        }
+        w[c] = (i == 0) ? u[c] : (u[c] + tmp);
+      }
+      small_field_n<SYS, D>(A, mn, rg, sc, w, f);
+#pragma unroll
+      for (int c = 0; c < D; c++) k[c][i] = h * f[c];
+    }
+#pragma unroll
+    for (int c = 0; c < D; c++) u[c] = u[c] + numpy_sum_bk<S>(k[c], T.b);
+  }
+#pragma unroll
+  for (int i = 0; i < D; i++) u1[s * ld1 + i] = u[i];
+}
+
+template <int SYS>
+__global__ void rhs_small_kernel(SysArgs A, int n, const double* __restrict__ u,
+                                 double* __restrict__ out) {
+  constexpr int D = SmallDim<SYS>::D;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double mn[D], rg[D], sc[D], w[D], f[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    mn[i] = A.normalize ? A.mn[i] : 0.0;
+    rg[i] = A.normalize ? (A.mx[i] - A.mn[i]) : 2.0;
+    sc[i] = 2.0 / rg[i];
+    w[i] = u[(long long)s * D + i];
+  }
+  small_field_n<SYS, D>(A, mn, rg, sc, w, f);
+#pragma unroll
+  for (int i = 0; i < D; i++) out[(long long)s * D + i] = f[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// PDE systems: one CTA per slice, one thread per grid point
+// ---------------------------------------------------------------------------------------
+// FitzHugh-Nagumo on a periodic d_x x d_x grid (systems.py:291-383).  State = [u1 | u2],
+// point p = iy*d_x + ix; DXX = kron(I, Dxx) couples ix+-1, DYY = kron(Dyy, I) couples iy+-1.
+// params: [d_x, a*diag, a*off, b*diag, b*off, k, 1/tau] -- the entries of a*(DXX+DYY) and
+// b*(DXX+DYY) computed on the host exactly as the reference builds its dense matrices.
+struct FhnPde {
+  static constexpr int NC = 2;
+  int pl, pr, pd, pu, npts;
+  __device__ void setup(const SysArgs& A, int p) {
+    const int dx = (int)A.p[0];
+    npts = dx * dx;
+    const int ix = p % dx, iy = p / dx;
+    pl = iy * dx + (ix == 0 ? dx - 1 : ix - 1);
+    pr = iy * dx + (ix == dx - 1 ? 0 : ix + 1);
+    pd = (iy == 0 ? dx - 1 : iy - 1) * dx + ix;
+    pu = (iy == dx - 1 ? 0 : iy + 1) * dx + ix;
+  }
+  __device__ static int points(const SysArgs& A) { return (int)A.p[0] * (int)A.p[0]; }
+  // buf holds the de-normalised stage input of every point: [u1 (npts) | u2 (npts)]
+  __device__ void eval(const SysArgs& A, const double* buf, int p, const double (&v)[2],
+                       double (&f)[2]) const {
+    const double* b1 = buf;
+    const double* b2 = buf + npts;
+    double m1 = A.p[2] * b1[pd];
+    m1 = m1 + A.p[2] * b1[pl];
+    m1 = m1 + A.p[1] * v[0];
+    m1 = m1 + A.p[2] * b1[pr];
+    m1 = m1 + A.p[2] * b1[pu];
+    double m2 = A.p[4] * b2[pd];
+    m2 = m2 + A.p[4] * b2[pl];
+    m2 = m2 + A.p[3] * v[1];
+    m2 = m2 + A.p[4] * b2[pr];
+    m2 = m2 + A.p[4] * b2[pu];
+    // U = a*(DXX+DYY)@u1 + u1 - u1**3 - u2 + k ;  V = (1/tau)*(b*(DXX+DYY)@u2 + u1 - u2)
+    f[0] = (((m1 + v[0]) - cube_cr(v[0])) - v[1]) + A.p[5];
+    f[1] = A.p[6] * ((m2 + v[0]) - v[1]);
+  }
+};
+
+// Viscous Burgers, periodic central differences (systems.py:402-450).
+// params: [Dxx_off, Dxx_diag, Dx_off]
+struct BurgersPde {
+  static constexpr int NC = 1;
+  int pl, pr, npts;
+  __device__ void setup(const SysArgs& A, int p) {
+    npts = A.d;
+    pl = (p == 0) ? npts - 1 : p - 1;
+    pr = (p == npts - 1) ? 0 : p + 1;
+  }
+  __device__ static int points(const SysArgs& A) { return A.d; }
+  __device__ void eval(const SysArgs& A, const double* buf, int p, const double (&v)[1],
+                       double (&f)[1]) const {
+    const double ul = buf[pl], ur = buf[pr];
+    double lap = A.p[0] * ul;
+    lap = lap + A.p[1] * v[0];
+    lap = lap + A.p[0] * ur;
+    const double adv = (-A.p[2]) * ul + A.p[2] * ur;
+    f[0] = lap - v[0] * adv;  // Dxx@u - u*(Dx@u)
+  }
+};
+
+template <class RHS, int S, int TB>
+__global__ void __launch_bounds__(TB)
+rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__ t0s,
+              const double* __restrict__ t1s, const double* __restrict__ u0, long long ld0,
+              double* __restrict__ u1, long long ld1) {
+  constexpr int NC = RHS::NC;
+  extern __shared__ double sm[];
+  const Tableau& T = c_tab[SlotOf<S>::value];
+  const int npts = RHS::points(A);
+  const int p = threadIdx.x;
+  const bool active = p < npts;
+  const int pp = active ? p : 0;
+  const long long s = blockIdx.x;
+  RHS rhs;
+  rhs.setup(A, pp);
+  double u[NC], mn[NC], rg[NC], sc[NC], k[NC][S];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    u[c] = u0[s * ld0 + c * npts + pp];
+    mn[c] = A.normalize ? A.mn[c * npts + pp] : 0.0;
+    rg[c] = A.normalize ? (A.mx[c * npts + pp] - A.mn[c * npts + pp]) : 2.0;
+    sc[c] = 2.0 / rg[c];
+  }
+  const double t0 = t0s[s], t1 = t1s[s];
+  const double step = (t1 - t0) / (double)steps;
+  int par = 0;
+  for (long long n = 0; n < steps; n++) {
+    const double h = step_size(h_mode, t0, t1, step, n, steps);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      double v[NC], f[NC];
+      double* buf = sm + par * (NC * npts);
+      par ^= 1;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        double tmp = 0.0;
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+          const double aij = T.a[i * NNGP_MAX_STAGES + j];
+          if (aij != 0.0) tmp = tmp + aij * k[c][j];
+        }
+        const double w = (i == 0) ? u[c] : (u[c] + tmp);
+        v[c] = A.normalize ? (((w + 1.0) / 2.0) * rg[c] + mn[c]) : w;
+        if (active) buf[c * npts + p] = v[c];
+      }
+      __syncthreads();
+      rhs.eval(A, buf, pp, v, f);
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (A.normalize) f[c] = f[c] * sc[c];
+        k[c][i] = h * f[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) u[c] = u[c] + numpy_sum_bk<S>(k[c], T.b);
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) u1[s * ld1 + c * npts + p] = u[c];
+  }
+}
+
+template <class RHS>
+__global__ void rhs_pde_kernel(SysArgs A, const double* __restrict__ uin,
+                               double* __restrict__ out) {
+  constexpr int NC = RHS::NC;
+  extern __shared__ double sm[];
+  const int npts = RHS::points(A);
+  const int p = threadIdx.x;
+  const bool active = p < npts;
+  const int pp = active ? p : 0;
+  const long long s = blockIdx.x;
+  RHS rhs;
+  rhs.setup(A, pp);
+  double v[NC], f[NC], rg[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const double w = uin[s * A.d + c * npts + pp];
+    const double mn = A.normalize ? A.mn[c * npts + pp] : 0.0;
+    rg[c] = A.normalize ? (A.mx[c * npts + pp] - A.mn[c * npts + pp]) : 2.0;
+    v[c] = A.normalize ? (((w + 1.0) / 2.0) * rg[c] + mn) : w;
+    if (active) sm[c * npts + p] = v[c];
+  }
+  __syncthreads();
+  rhs.eval(A, sm, pp, v, f);
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      out[s * A.d + c * npts + p] = A.normalize ? f[c] * (2.0 / rg[c]) : f[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+SysArgs nngp_sys_args(const SystemDesc& s) {
+  SysArgs A;
+  A.system_id = s.system_id;
+  A.d = s.d;
+  A.normalize = s.normalize;
+  for (int i = 0; i < NNGP_MAX_PARAMS; i++) A.p[i] = s.params[i];
+  A.mn = s.d_mn;
+  A.mx = s.d_mx;
+  return A;
+}
+
+template <int SYS>
+static void launch_small(const SysArgs& A, int method, int h_mode, long long steps,
+                         int n, const double* t0, const double* t1, const double* u0,
+                         long long ld0, double* u1, long long ld1, cudaStream_t st) {
+  const int threads = 32;
+  const int blocks = (n + threads - 1) / threads;
+  switch (method) {
+    case 1: rk_small_kernel<SYS, 1><<<blocks, threads, 0, st>>>(A, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1); break;
+    case 2: rk_small_kernel<SYS, 2><<<blocks, threads, 0, st>>>(A, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1); break;
+    case 4: rk_small_kernel<SYS, 4><<<blocks, threads, 0, st>>>(A, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1); break;
+    default: rk_small_kernel<SYS, 11><<<blocks, threads, 0, st>>>(A, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1); break;
+  }
+}
+
+template <class RHS, int TB>
+static void launch_pde_tb(const SysArgs& A, int npts, int method, int h_mode, long long steps,
+                          int n, const double* t0, const double* t1, const double* u0,
+                          long long ld0, double* u1, long long ld1, cudaStream_t st) {
+  const int threads = ((npts + 31) / 32) * 32;
+  const size_t smem = 2 * sizeof(double) * RHS::NC * npts;
+  switch (method) {
+    case 1: rk_pde_kernel<RHS, 1, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 2: rk_pde_kernel<RHS, 2, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 4: rk_pde_kernel<RHS, 4, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    default: rk_pde_kernel<RHS, 11, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+  }
+}
+
+template <class RHS>
+static void launch_pde(const SysArgs& A, int npts, int method, int h_mode, long long steps,
+                       int n, const double* t0, const double* t1, const double* u0,
+                       long long ld0, double* u1, long long ld1, cudaStream_t st) {
+  if (npts <= 256)
+    launch_pde_tb<RHS, 256>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+  else
+    launch_pde_tb<RHS, 1024>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+}
+
+static int check_system(nngp_handle_t h, const SystemDesc& s, int* npts) {
+  *npts = 0;
+  switch (s.system_id) {
+    case NNGP_SYS_FHN_ODE: case NNGP_SYS_BRUSSELATOR:
+      if (s.d != 2) return nngp_fail(h, "system %d needs d=2, got %d", s.system_id, s.d);
+      return 0;
+    case NNGP_SYS_ROSSLER: case NNGP_SYS_HOPF: case NNGP_SYS_LORENZ: case NNGP_SYS_THOMAS:
+      if (s.d != 3) return nngp_fail(h, "system %d needs d=3, got %d", s.system_id, s.d);
+      return 0;
+    case NNGP_SYS_DBLPEND:
+      if (s.d != 4) return nngp_fail(h, "system %d needs d=4, got %d", s.system_id, s.d);
+      return 0;
+    case NNGP_SYS_FHN_PDE: {
+      const int dx = (int)s.params[0];
+      if (dx < 3 || 2 * dx * dx != s.d) return nngp_fail(h, "FHN_PDE: d=%d is not 2*d_x^2 (d_x=%d)", s.d, dx);
+      if (dx * dx > 1024) return nngp_fail(h, "FHN_PDE: d_x^2=%d > 1024 grid points per CTA", dx * dx);
+      *npts = dx * dx;
+      return 0;
+    }
+    case NNGP_SYS_BURGERS:
+      if (s.d < 3 || s.d > 1024) return nngp_fail(h, "Burgers: d=%d outside [3,1024]", s.d);
+      *npts = s.d;
+      return 0;
+    default:
+      return nngp_fail(h, "unknown system id %d", s.system_id);
+  }
+}
+
+int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long long steps,
+              int n_slices, const double* d_t0, const double* d_t1, const double* d_u0,
+              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st) {
+  const int slot = method_slot(method);
+  if (slot < 0) return nngp_fail(h, "Only RK1, RK2, RK4 and RK8 are implemented (got %d)", method);
+  if (steps < 1) return nngp_fail(h, "steps must be >= 1 (got %lld)", steps);
+  if (h_mode != NNGP_H_LINSPACE && h_mode != NNGP_H_CONST) return nngp_fail(h, "bad h_mode %d", h_mode);
+  if (n_slices <= 0) return 0;
+  int npts = 0;
+  if (int rc = check_system(h, s, &npts)) return rc;
+  const SysArgs A = nngp_sys_args(s);
+#define SMALL(SYS) launch_small<SYS>(A, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st)
+  switch (s.system_id) {
+    case NNGP_SYS_FHN_ODE: SMALL(NNGP_SYS_FHN_ODE); break;
+    case NNGP_SYS_ROSSLER: SMALL(NNGP_SYS_ROSSLER); break;
+    case NNGP_SYS_HOPF: SMALL(NNGP_SYS_HOPF); break;
+    case NNGP_SYS_DBLPEND: SMALL(NNGP_SYS_DBLPEND); break;
+    case NNGP_SYS_BRUSSELATOR: SMALL(NNGP_SYS_BRUSSELATOR); break;
+    case NNGP_SYS_LORENZ: SMALL(NNGP_SYS_LORENZ); break;
+    case NNGP_SYS_THOMAS: SMALL(NNGP_SYS_THOMAS); break;
+    case NNGP_SYS_FHN_PDE:
+      launch_pde<FhnPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+      break;
+    case NNGP_SYS_BURGERS:
+      launch_pde<BurgersPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+      break;
+  }
+#undef SMALL
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int rhs_launch(nngp_handle_t h, const SystemDesc& s, int n, const double* d_u, double* d_out,
+               cudaStream_t st) {
+  if (n <= 0) return 0;
+  int npts = 0;
+  if (int rc = check_system(h, s, &npts)) return rc;
+  const SysArgs A = nngp_sys_args(s);
+  const int tb = 128, nb = (n + tb - 1) / tb;
+  switch (s.system_id) {
+    case NNGP_SYS_FHN_ODE: rhs_small_kernel<NNGP_SYS_FHN_ODE><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_ROSSLER: rhs_small_kernel<NNGP_SYS_ROSSLER><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_HOPF: rhs_small_kernel<NNGP_SYS_HOPF><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_DBLPEND: rhs_small_kernel<NNGP_SYS_DBLPEND><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_BRUSSELATOR: rhs_small_kernel<NNGP_SYS_BRUSSELATOR><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_LORENZ: rhs_small_kernel<NNGP_SYS_LORENZ><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_THOMAS: rhs_small_kernel<NNGP_SYS_THOMAS><<<nb, tb, 0, st>>>(A, n, d_u, d_out); break;
+    case NNGP_SYS_FHN_PDE: {
+      const int threads = ((npts + 31) / 32) * 32;
+      rhs_pde_kernel<FhnPde><<<n, threads, sizeof(double) * 2 * npts, st>>>(A, d_u, d_out);
+      break;
+    }
+    case NNGP_SYS_BURGERS: {
+      const int threads = ((npts + 31) / 32) * 32;
+      rhs_pde_kernel<BurgersPde><<<n, threads, sizeof(double) * npts, st>>>(A, d_u, d_out);
+      break;
+    }
+  }
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
