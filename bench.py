@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- one nnGParareal iteration of the FHN-PDE target (BASELINE.json configs[3]) on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+A "step" is ONE nnGParareal iteration (parareal.py:301-439) from the state after the coarse
+initialisation: fine solves of all N slices (batched RK8, sharded by slice over the ranks + one
+all-gather), dataset append, the serial sweep (G + kNN + d*9 Nelder-Mead GP fits + prediction per
+slice) and the per-slice convergence norms.  `value` = iterations per second with every input
+resident in HBM; `e2e` = the same iteration through the reference-facing Python protocols
+(CudaPool.map(solver.run_F_timed) / model.fit / solver.run_G_timed / model.predict_timed) on HOST
+buffers, host<->device copies inside the timed region.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Parareal iters/sec + nnGP fits/sec, FHN PDE N=512, 1-8 B200 vs CPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dx", type=int, default=16, help="FHN grid side (d = 2*dx^2)")
+    ap.add_argument("--slices", type=int, default=512)
+    ap.add_argument("--m", type=int, default=20, help="nearest neighbours (nn)")
+    ap.add_argument("--fine-steps", type=int, default=195325,
+                    help="RK8 steps per slice; 195325 = the published run (FHN_PDE.py:53-54), 25 = configs.py preset")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel-class event timings here (json)")
+    return ap.parse_args()
+
+
+def nll_flops(m):
+    """algorithmic FP64 operations of one objective evaluation:
+    m^3/3 + 2 m^2 + 3 m(m+1)/2 + 4 m with exp / log / sqrt / div counted as one each"""
+    return m ** 3 / 3 + 2 * m ** 2 + 3 * m * (m + 1) / 2 + 4 * m
+
+
+def rk_flops(d, S, rhs_per_point=26):
+    """algorithmic FP64 operations of one RK step of one slice: S stencil RHS
+    (26 per grid point pair) + dense-tableau combinations as the reference evaluates them"""
+    return S * rhs_per_point * (d / 2) + (S * (S - 1) / 2) * 2 * d + S * 2 * d + 2 * S * d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(args, n_dims_per_core, n_steps, warm):
+    """oracle (NumPy/SciPy port of the reference) on all host cores; returns the list of samples"""
+    import warnings
+    from oracle.cpu_baseline import FhnCpuSampler
+    warnings.filterwarnings("ignore")
+    cores = os.cpu_count()
+    T = 1100.0 * args.slices / 512 if args.dx == 16 else 1100.0
+    s = FhnCpuSampler(d_x=args.dx, N=args.slices, m=args.m, T=T, cores=cores)
+    d = 2 * args.dx * args.dx
+    n_dims = min(d, max(cores, n_dims_per_core * cores))
+    out = []
+    for it in range(warm + n_steps):
+        t0 = time.perf_counter()
+        r = s.sample(n_dims=n_dims, n_slices=min(args.slices, cores), fine_steps=args.fine_steps)
+        r["wall"] = time.perf_counter() - t0
+        if it >= warm:
+            out.append(r)
+    s.close()
+    return out, cores, n_dims
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port), rank 0 only"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    samples, cores, n_dims = cpu_sample(args, n_dims_per_core=2, n_steps=args.steps, warm=min(args.warmup, 1))
+    t_iter = float(np.mean([r["t_iter"] for r in samples]))
+    d = 2 * args.dx * args.dx
+    sample = (f"per step: one predict restricted to {n_dims} of {d} output dims ({n_dims*9} Nelder-Mead searches) "
+              f"farmed over {cores} processes + {min(args.slices, cores)} fine slices of 25 RK8 steps scaled to "
+              f"{args.fine_steps}; extrapolated with T_iter = ceil(N/C) t_F + (N-1)(t_G + t_predict)")
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / t_iter, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "gpu_launches": 0,
+            "fits_per_s": float(np.mean([r["fits_per_s"] for r in samples])),
+            "cpu_s_per_nm_run": float(np.mean([r["cpu_s_per_nm_run"] for r in samples])),
+            "t_F_slice_s": float(np.mean([r["t_F_slice"] for r in samples])),
+            "t_predict_s": float(np.mean([r["t_predict"] for r in samples])),
+            "cpu_baseline": {"value": 1.0 / t_iter, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": 1.0 / t_iter, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    d = 2 * args.dx * args.dx
+    return {"workload": f"FHN-PDE {args.dx}x{args.dx} (d={d}) nnGParareal, one iteration from the coarse initialisation",
+            "N_slices": args.slices, "d": d, "m": args.m, "n_restarts": 1, "jitters": 9, "G": "RK4 x25 steps/slice",
+            "F": f"RK8 x{args.fine_steps} steps/slice", "seed": 45, "epsilon": 5e-7,
+            "l2": "256 MiB write between timed steps (L2 flush)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import nearest_neighbors_gparareal_b200 as nn
+    from nearest_neighbors_gparareal_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = _lib.default_handle(local)
+
+    # ---- the workload: configs.py fhn_pde preset with the requested number of fine steps ----------
+    N, m = args.slices, args.m
+    ode = nn.FHN_PDE(d_x=args.dx)
+    d = ode.get_dim()
+    cfg = nn.Config(ode, d_x=args.dx).get()
+    cfg["N"] = N
+    cfg["tspan"] = [0, cfg["tspan"][1] * N / 512]
+    cfg["Nf"] = args.fine_steps
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+    par = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=N, epsilon=5e-7, verbose="")
+    model = nn.CudaNNGP(n=d, N=N, nn=m, seed=45, handle=h)
+    st = par.device_setup(model)
+    torch.cuda.synchronize(dev)
+    u0_cur, uG0_cur = st["u_cur"].clone(), st["uG_cur"].clone()
+    starts_host = model.draw_starts(N - 1)
+    starts = torch.from_numpy(starts_host).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        st["I"] = 0
+        st["u_cur"].copy_(u0_cur)
+        st["uG_cur"].copy_(uG0_cur)
+        st["u_next"].copy_(u0_cur)
+        st["uG_next"].copy_(uG0_cur)
+        h.dataset_reset()
+        par.device_fine_step(st)
+        par.device_sweep(st, 0, starts=starts)
+        return par.device_errors(st)  # the one device->host read of an iteration (N+1 doubles)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        err = step()
+        flush.fill_(1)
+    h.counters(reset=True)
+    h.profile_read(reset=True)
+    h.profile_enable(True)
+    launches0 = h.launch_count()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        err = step()
+        flush.fill_(1)
+    ev[1].record()
+    sync_all()
+    clk = clocks.stop()
+    ms_total = ev[0].elapsed_time(ev[1])
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    h.profile_enable(False)
+    prof = h.profile_read(reset=True)
+    nm_runs, nll_evals = h.counters(reset=True)
+    launches = (h.launch_count() - launches0) // args.steps
+
+    # ---- roofline of the dominant kernel (GP fit: FP64 pipe) --------------------------------------
+    fp64_peak = h.bench_fp64(20000)
+    fit_ms, fit_n = prof["gp_fit"]
+    rk_ms, rk_n = prof["rk"]
+    flops_fit = nll_evals * nll_flops(m)
+    fit_tf = flops_fit / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0
+    roofline = {"kernel": "gp_fit_predict_kernel", "bound": "fp64", "achieved": fit_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": fit_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "FP64 FMA micro-benchmark run in this process (nngp_bench_fp64); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "per_launch": {"launches": fit_n // args.steps, "avg_ms": fit_ms / max(fit_n, 1),
+                               "nll_evals": nll_evals / max(fit_n, 1), "flops_per_eval": nll_flops(m)},
+                "share_of_step": fit_ms / (ms_step * args.steps)}
+    # the fine propagator launch (first rk launch of each step carries all slices)
+    f_flops = rk_flops(d, 11) * args.fine_steps * math.ceil(N / world)
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] // args.steps} for k, v in prof.items()}
+
+    sweep_ms = sum(prof[k][0] for k in ("knn", "gp_prep", "gp_fit")) / args.steps
+    line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "clocks": clk, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+            "fits_per_s": (N - 1) * d / (ms_step * 1e-3), "nm_runs_per_s": nm_runs / args.steps / (ms_step * 1e-3),
+            "nll_evals_per_s": nll_evals / args.steps / (ms_step * 1e-3),
+            "nll_evals_per_nm_run": nll_evals / max(nm_runs, 1),
+            "fine_step_flops_per_rank": f_flops, "err_max_iter0": float(np.nanmax(err))}
+
+    # ---- e2e: the same iteration through the reference-facing protocols on host buffers -----------
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(args, nn, ode, solver, cfg, h, dev, world, rank, sync_all, dist)
+    # ---- CPU baseline: the oracle port on this host's cores (rank 0, N=1 only) --------------------
+    if world == 1 and not args.no_cpu_baseline:
+        samples, cores, n_dims = cpu_sample(args, n_dims_per_core=8, n_steps=1, warm=0)
+        r = samples[0]
+        line["cpu_baseline"] = {
+            "value": 1.0 / r["t_iter"], "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": (f"one predict restricted to {n_dims} of {d} dims ({n_dims*9} Nelder-Mead searches, "
+                       f"{r['cpu_s_per_nm_run']*1e3:.1f} ms each) on {cores} processes + {r['n_slices']} fine slices of "
+                       f"25 RK8 steps scaled to {args.fine_steps}; T_iter = ceil(N/C) t_F + (N-1)(t_G + t_predict); "
+                       f"sample wall {r['wall']:.1f} s"),
+            "fits_per_s": r["fits_per_s"], "t_F_slice_s": r["t_F_slice"], "t_predict_s": r["t_predict"]}
+    if rank == 0:
+        if args.profile_out:
+            with open(args.profile_out, "w") as fh:
+                json.dump(line, fh, indent=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, nn, ode, solver, cfg, h, dev, world, rank, sync_all, dist):
+    """One iteration through Parareal's protocols: pool.map(run_F_timed) -> fit -> (run_G_timed, predict_timed)*"""
+    import torch
+    N, d, m = args.slices, ode.get_dim(), args.m
+    t = np.linspace(cfg["tspan"][0], cfg["tspan"][1], N + 1)
+    pool = nn.CudaPool(sharded=(world > 1))
+    # state after the coarse initialisation, on the host
+    u_cur = np.empty((N + 1, d))
+    u_cur[0] = ode.get_init_cond()
+    for i in range(N):
+        u_cur[i + 1] = solver.run_G(t[i], t[i + 1], u_cur[i])
+    uG_cur = u_cur.copy()
+    h2d = d2h = 0
+
+    def iteration():
+        nonlocal h2d, d2h
+        model = nn.CudaNNGP(n=d, N=N, nn=m, seed=45, handle=h)
+        res = list(pool.map(solver.run_F_timed, t[0:N], t[1:N + 1], [u_cur[i] for i in range(N)]))
+        uF = np.empty((N + 1, d))
+        uF[0] = u_cur[0]
+        uF[1:] = np.array([r[0] for r in res])
+        n_loc = math.ceil(N / world)
+        h2d += (n_loc * d + 2 * n_loc) * 8
+        d2h += n_loc * d * 8
+        u_next, uG_next = u_cur.copy(), uG_cur.copy()
+        u_next[1] = uF[1]
+        x = u_cur[0:N]
+        D = uF[1:N + 1] - uG_cur[1:N + 1]
+        model.fit_timed(x, D, k=0)
+        h2d += 2 * x.size * 8
+        for i in range(1, N):
+            uG_next[i + 1], _ = solver.run_G_timed(t[i], t[i + 1], u_next[i])
+            preds = model.predict_timed(u_next[i].reshape(1, -1), uF[i + 1], uG_cur[i + 1], i=i)
+            u_next[i + 1] = preds + uG_next[i + 1]
+            h2d += (d + 2) * 8 + d * 8 + d * 9 * 2
+            d2h += 2 * d * 8
+        return np.linalg.norm(u_next - u_cur, np.inf, 1)
+
+    iteration()  # warm-up
+    h2d = d2h = 0
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        err = iteration()
+    sync_all()
+    secs = (time.perf_counter() - t0) / args.e2e_steps
+    tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    secs = float(tt.item())
+    return {"value": 1.0 / secs, "unit": "iters/s", "ms_per_step": 1e3 * secs, "steps": args.e2e_steps,
+            "h2d_bytes_per_step": int(h2d // args.e2e_steps), "d2h_bytes_per_step": int(d2h // args.e2e_steps),
+            "fits_per_s": (N - 1) * d / secs, "err_max_iter0": float(np.nanmax(err)),
+            "api": "CudaPool.map(solver.run_F_timed) + CudaNNGP.fit_timed + per slice CudaSolverRK.run_G_timed / "
+                   "CudaNNGP.predict_timed (NumPy in, NumPy out)"}
+
+
+if __name__ == "__main__":
+    main()

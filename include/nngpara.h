@@ -145,6 +145,14 @@ int nngp_rowwise_maxabs_diff(nngp_handle_t h, const double* d_a, const double* d
 
 /* counters of kernel launches issued through this handle (bench.py: gpu_launches) */
 long long nngp_launch_count(nngp_handle_t h);
+/* device-side work counters since the last reset (synchronises): Nelder-Mead searches run and
+ * objective (negative log marginal likelihood) evaluations made -- models.py:254-260, 240-252 */
+int nngp_counters(nngp_handle_t h, long long* nm_runs, long long* nll_evals, int reset);
+/* per-kernel-class device time measured with CUDA events on the launching stream while enabled;
+ * classes: 0 RK propagators, 1 kNN, 2 neighbour distance matrix, 3 GP fit+predict, 4 other.
+ * nngp_profile_read synchronises; ms[5] accumulated milliseconds, counts[5] timed launches. */
+int nngp_profile_enable(nngp_handle_t h, int on);
+int nngp_profile_read(nngp_handle_t h, double* ms, long long* counts, int reset);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,9 @@ SIGNATURES = {
     "nngp_append_iteration": (ci, [vp, vp, vp, vp, ci, ci, ci, vp]),
     "nngp_rowwise_maxabs_diff": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "nngp_launch_count": (cll, [vp]),
+    "nngp_counters": (ci, [vp, c_ll_p, c_ll_p, ci]),
+    "nngp_profile_enable": (ci, [vp, ci]),
+    "nngp_profile_read": (ci, [vp, vp, vp, ci]),
 }
 
 SYSTEM_IDS = {"FHN_ODE": 0, "Rossler": 1, "Hopf": 2, "DblPend": 3, "Brusselator": 4, "Lorenz": 5,
@@ -255,6 +258,23 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.nngp_launch_count(self.h))
+
+    def counters(self, reset=False):
+        """(Nelder-Mead runs, objective evaluations) since the last reset"""
+        a, b = cll(0), cll(0)
+        self.check(self.lib.nngp_counters(self.h, ctypes.byref(a), ctypes.byref(b), 1 if reset else 0))
+        return a.value, b.value
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.nngp_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        """{class: (milliseconds, launches)} for rk / knn / gp_prep / gp_fit / other"""
+        ms = np.zeros(5)
+        cnt = np.zeros(5, dtype=np.int64)
+        self.check(self.lib.nngp_profile_read(self.h, _ptr(ms), _ptr(cnt), 1 if reset else 0))
+        names = ("rk", "knn", "gp_prep", "gp_fit", "other")
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(names)}
 
     def bench_fp64(self, iters=20000):
         out = cd(0.0)

@@ -19,6 +19,26 @@ int nngp_fail(nngp_handle_t h, const char* fmt, ...) {
 
 static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
+ProfScope::ProfScope(nngp_handle_t h_, int cls, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
+  if (!on) return;
+  nngp_handle_s::ProfRec r;
+  r.cls = cls;
+  for (cudaEvent_t* e : {&r.a, &r.b}) {
+    if (!h->prof_free.empty()) {
+      *e = h->prof_free.back();
+      h->prof_free.pop_back();
+    } else {
+      cudaEventCreate(e);
+    }
+  }
+  cudaEventRecord(r.a, st);
+  h->prof_recs.push_back(r);
+}
+
+ProfScope::~ProfScope() {
+  if (on) cudaEventRecord(h->prof_recs.back().b, st);
+}
+
 void* nngp_workspace(nngp_handle_t h, size_t bytes) {
   if (bytes <= h->ws_bytes) return h->ws;
   // grow: work already enqueued may still use the old block
@@ -102,6 +122,11 @@ int nngp_create(int device, nngp_handle_t* out) {
     delete h;
     return nngp_fail(nullptr, "cudaStreamCreate failed");
   }
+  if (cudaMalloc(&h->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(h->d_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+    delete h;
+    return nngp_fail(nullptr, "cudaMalloc(counters) failed");
+  }
   if (rk_set_tableaus(h) != 0) {
     g_create_error = h->err;
     delete h;
@@ -126,6 +151,9 @@ int nngp_destroy(nngp_handle_t h) {
   if (h->stage) cudaFree(h->stage);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->d_counters) cudaFree(h->d_counters);
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->prof_free) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -138,6 +166,42 @@ int nngp_synchronize(nngp_handle_t h, void* stream) {
 }
 
 long long nngp_launch_count(nngp_handle_t h) { return h->launches; }
+
+int nngp_counters(nngp_handle_t h, long long* nm_runs, long long* nll_evals, int reset) {
+  unsigned long long v[2];
+  NNGP_CUDA(h, cudaDeviceSynchronize());
+  NNGP_CUDA(h, cudaMemcpy(v, h->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+  if (nm_runs) *nm_runs = (long long)v[0];
+  if (nll_evals) *nll_evals = (long long)v[1];
+  if (reset) NNGP_CUDA(h, cudaMemset(h->d_counters, 0, sizeof(v)));
+  return 0;
+}
+
+int nngp_profile_enable(nngp_handle_t h, int on) {
+  h->profiling = (on != 0);
+  return 0;
+}
+
+int nngp_profile_read(nngp_handle_t h, double* ms, long long* counts, int reset) {
+  NNGP_CUDA(h, cudaDeviceSynchronize());
+  for (auto& r : h->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      h->prof_ms[r.cls] += t;
+      h->prof_n[r.cls] += 1;
+    }
+    h->prof_free.push_back(r.a);
+    h->prof_free.push_back(r.b);
+  }
+  cudaGetLastError();
+  h->prof_recs.clear();
+  for (int i = 0; i < NNGP_PROF_CLASSES; i++) {
+    if (ms) ms[i] = h->prof_ms[i];
+    if (counts) counts[i] = h->prof_n[i];
+    if (reset) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  }
+  return 0;
+}
 
 // ---- systems ---------------------------------------------------------------------------
 int nngp_system_create(nngp_handle_t h, int system_id, int d, const double* params, int n_params,

@@ -10,6 +10,7 @@
 
 #define NNGP_MAX_PARAMS 8
 #define NNGP_MAX_STAGES 11
+#define NNGP_PROF_CLASSES 5  // 0 rk, 1 knn, 2 gp_prep, 3 gp_fit, 4 other
 
 struct SystemDesc {
   int system_id = -1;
@@ -51,6 +52,24 @@ struct nngp_handle_s {
   void* stage = nullptr;  // device staging for *_host variants
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
+  unsigned long long* d_counters = nullptr;
+  // optional per-kernel-class timing with CUDA events on the launching stream
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_free;
+  double prof_ms[NNGP_PROF_CLASSES] = {0};
+  long long prof_n[NNGP_PROF_CLASSES] = {0};
+};
+
+// RAII: times the launches issued inside its scope when profiling is on
+struct ProfScope {
+  nngp_handle_t h;
+  cudaStream_t st;
+  bool on;
+  ProfScope(nngp_handle_t h_, int cls, cudaStream_t st_);
+  ~ProfScope();
 };
 
 int nngp_fail(nngp_handle_t h, const char* fmt, ...);

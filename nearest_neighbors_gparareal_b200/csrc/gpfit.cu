@@ -320,6 +320,7 @@ struct FitArgs {
   int* nfev;              // [nq,d,9,R]
   double* fvals;          // [nq,d,9,R]
   double* thetas;         // [nq,d,9,R,2]
+  unsigned long long* counters;  // [0] NM runs, [1] nll evaluations
   int d, m, R;
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
@@ -382,6 +383,8 @@ gp_fit_predict_kernel(FitArgs A) {
       rf[run] = o.f;
       rt[2 * run] = o.x0;
       rt[2 * run + 1] = o.x1;
+      atomicAdd(A.counters, 1ULL);
+      atomicAdd(A.counters + 1, (unsigned long long)o.nfev);
       if (A.nfev) A.nfev[task0 + run] = o.nfev;
       if (A.fvals) A.fvals[task0 + run] = o.f;
       if (A.thetas) {
@@ -541,6 +544,7 @@ size_t gp_prep_bytes(int nq, int m) { return sizeof(double) * (size_t)nq * m * m
 int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, double* d_r2,
                    cudaStream_t st) {
   if (nq <= 0) return 0;
+  ProfScope prof(h, 2, st);
   gp_prep_kernel<<<nq, 256, 0, st>>>(d_idx, h->ds_x, h->ds_d, m, d_r2);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
@@ -561,6 +565,7 @@ static int fit_launch_m(nngp_handle_t h, const FitArgs& A, int nq, cudaStream_t 
     NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_predict_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  ProfScope prof(h, 3, st);
   gp_fit_predict_kernel<M><<<dim3(A.d, nq), GP_WARPS * 32, smem, st>>>(A);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
@@ -587,7 +592,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   FitArgs A;
   A.idx = d_idx; A.dist = d_dist; A.r2 = d_r2; A.Y = h->ds_y; A.starts = d_starts; A.add = d_add;
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
-  A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas;
+  A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
   A.d = h->ds_d; A.m = m; A.R = R; A.ld_pred = h->ds_d; A.fatol = fatol; A.xatol = xatol;
   int rc = 0;
   DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, nq, st));

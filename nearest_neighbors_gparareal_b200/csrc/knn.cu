@@ -59,6 +59,7 @@ static int append_common(nngp_handle_t h, const double* xs, long long ldx, const
   if (h->ds_rows + rows > h->ds_cap)
     return nngp_fail(h, "dataset capacity exceeded: %lld + %lld > %lld", h->ds_rows, rows, h->ds_cap);
   const int d = h->ds_d;
+  ProfScope prof(h, 4, st);
   dim3 block(32, 8);
   dim3 grid((d + 31) / 32, (unsigned)((rows + 31) / 32));
   append_kernel<<<grid, block, 0, st>>>(xs, ldx, ya, yb, ldy, rows, d, h->ds_rows, h->ds_cap,
@@ -258,6 +259,7 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
   if (n < m) return nngp_fail(h, "knn: dataset has %lld rows, fewer than m=%d", n, m);
   const int d = h->ds_d;
   double* dist = (double*)ws;
+  ProfScope prof(h, 1, st);
   const int tb = 128;
   const unsigned gx = (unsigned)((n + tb - 1) / tb);
   const size_t qrow = (size_t)d * sizeof(double), lim = 48 * 1024;

@@ -565,6 +565,7 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
   int npts = 0;
   if (int rc = check_system(h, s, &npts)) return rc;
   const SysArgs A = nngp_sys_args(s);
+  ProfScope prof(h, 0, st);
 #define SMALL(SYS) launch_small<SYS>(A, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st)
   switch (s.system_id) {
     case NNGP_SYS_FHN_ODE: SMALL(NNGP_SYS_FHN_ODE); break;

@@ -21,6 +21,26 @@ from .solver import CudaSolverRK, SolverAbstr
 from .systems import ODE
 
 
+def slice_block(I, N, rank, world):
+    """Contiguous block of the unconverged slices I..N-1 owned by `rank`: (chunk, first, count)."""
+    n_act = N - I
+    chunk = (n_act + world - 1) // world
+    lo = min(I + rank * chunk, N)
+    cnt = max(0, min(chunk, N - lo))
+    return chunk, lo, cnt
+
+
+def gather_fine_rows(uF, I, chunk, rank, world, group=None):
+    """The one collective of an iteration: every rank wrote rows uF[lo+1 : lo+1+cnt] of its block;
+    afterwards all ranks hold uF[I+1 : N+1].  uF needs world*chunk rows after row I."""
+    import torch.distributed as dist
+    view = uF[I + 1:I + 1 + world * chunk]
+    mine = view[rank * chunk:(rank + 1) * chunk]
+    if dist.get_backend(group) != 'nccl':
+        mine = mine.clone()  # gloo (CPU tests) does not take an input aliasing the output
+    dist.all_gather_into_tensor(view, mine, group=group)
+
+
 class Parareal():
     def __init__(self, ode, solver, tspan, N, epsilon=5e-7, verbose='v', **kwargs):
         if not isinstance(ode, ODE):
@@ -219,52 +239,117 @@ class PararealDevice(Parareal):
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
-    def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, return_data=True,
-                  max_rows=None, **kwargs):
+    # ---- device state ------------------------------------------------------------------
+    def device_setup(self, model, max_rows=None):
+        """Allocates the device-resident state and runs the coarse initialisation
+        (parareal.py:233-277).  Returns a dict that `device_iteration` advances."""
         import torch
-        if store_int:
-            raise NotImplementedError('intermediate checkpoints are outside the hot path')
         if not isinstance(model, (CudaNNGP, BareParareal)):
             raise Exception('PararealDevice supports the nngp and parareal models')
-        N, eps, n = self.N, self.epsilon, self.n
+        N, n = self.N, self.n
         solver = self.solver
         h, sysid = solver.device()
         dev = torch.device('cuda', h.device)
         rank, world = self._world()
-        verbose = kwargs.get('verbose', self.verbose)
-        mF, mG = _lib.METHODS[solver.F], _lib.METHODS[solver.G]
         if max(solver.Nf, solver.Ng) > solver.thresh:
             raise Exception('steps > thresh (RK paging, solver.py:89-96) is only supported by the host driver')
-        stream = torch.cuda.current_stream(dev).cuda_stream
         f64 = dict(dtype=torch.float64, device=dev)
-        t_host = np.linspace(self.tspan[0], self.tspan[1], num=N + 1)
-        d_t = torch.from_numpy(t_host).to(dev)
-        pad = world  # the in-place all-gather view may run past row N
-        u_cur = torch.zeros((N + 1, n), **f64)
-        uG_cur = torch.zeros((N + 1, n), **f64)
-        uF = torch.zeros((N + 1 + N + pad, n), **f64)
+        st = dict(h=h, sys=sysid, dev=dev, rank=rank, world=world, model=model,
+                  mF=_lib.METHODS[solver.F], mG=_lib.METHODS[solver.G],
+                  stream=torch.cuda.current_stream(dev).cuda_stream, is_gp=isinstance(model, CudaNNGP))
+        st['t_host'] = np.linspace(self.tspan[0], self.tspan[1], num=N + 1)
+        st['t'] = torch.from_numpy(st['t_host']).to(dev)
         u0 = torch.from_numpy(self.u0).to(dev)
-        u_cur[0] = u0
-        uG_cur[0] = u0
-        uF[0] = u0
-        d_err = torch.zeros(N + 1, **f64)
-        is_gp = isinstance(model, CudaNNGP)
-        if is_gp:
+        st['u_cur'] = torch.zeros((N + 1, n), **f64)
+        st['uG_cur'] = torch.zeros((N + 1, n), **f64)
+        # rows past N are scratch for the in-place all-gather of the last rank's padded block
+        st['uF'] = torch.zeros((N + 1 + N + world, n), **f64)
+        st['err'] = torch.zeros(N + 1, **f64)
+        for key in ('u_cur', 'uG_cur', 'uF'):
+            st[key][0] = u0
+        if st['is_gp']:
             model._handle = h
             h.dataset_reset()
-            h.dataset_reserve(max_rows or min(N * (N + 3) // 2 + 1, N * 64), n)
+            st['cap'] = max_rows or min(N * (N + 3) // 2 + 1, N * 16)
+            h.dataset_reserve(st['cap'], n)
             model._n_dev = 0
-        G_time = F_time = sweep_time = 0.0
+        for i in range(N):  # N dependent one-slice launches
+            h.rk_batch(sysid, st['mG'], solver.h_mode, solver.Ng, 1, st['t'][i:], st['t'][i + 1:],
+                       st['uG_cur'][i], n, st['uG_cur'][i + 1], n, st['stream'])
+        st['u_cur'].copy_(st['uG_cur'])
+        st['u_next'] = st['u_cur'].clone()
+        st['uG_next'] = st['uG_cur'].clone()
+        st['I'] = 0
+        st['times'] = dict(F=0.0, sweep=0.0)
+        return st
+
+    def device_fine_step(self, st):
+        """parareal.py:309-334: fine solves of slices I..N-1 (sharded by slice over the ranks, one
+        all-gather), then slice I+1 becomes exact."""
+        N, n, solver = self.N, self.n, self.solver
+        h, I, rank, world = st['h'], st['I'], st['rank'], st['world']
+        if world == 1:
+            h.rk_batch(st['sys'], st['mF'], solver.h_mode, solver.Nf, N - I, st['t'][I:], st['t'][I + 1:],
+                       st['u_cur'][I], n, st['uF'][I + 1], n, st['stream'])
+        else:
+            chunk, lo, cnt = slice_block(I, N, rank, world)
+            if cnt > 0:
+                h.rk_batch(st['sys'], st['mF'], solver.h_mode, solver.Nf, cnt, st['t'][lo:], st['t'][lo + 1:],
+                           st['u_cur'][lo], n, st['uF'][lo + 1], n, st['stream'])
+            gather_fine_rows(st['uF'], I, chunk, rank, world, self.group)
+        st['u_next'][I + 1].copy_(st['uF'][I + 1])
+        st['uG_next'][I + 1].copy_(st['uG_cur'][I + 1])
+        st['I'] = I + 1
+
+    def device_sweep(self, st, k, starts=None):
+        """parareal.py:336-382: dataset append + the serial sweep, all on the device.
+        `starts` (device int8 [(N-I), d, 9, R, 2]) may be passed in when already resident."""
+        import torch
+        N, n, solver = self.N, self.n, self.solver
+        h, I, model = st['h'], st['I'], st['model']
+        if st['is_gp']:
+            if h.dataset_rows() + (N - I + 1) > st['cap']:
+                st['cap'] = 2 * st['cap'] + N
+                h.dataset_reserve(st['cap'], n)
+            h.append_iteration(st['u_cur'], st['uF'], st['uG_cur'], N, I, n, st['stream'])
+            model._n_dev = h.dataset_rows()
+        if I == N:
+            return
+        if st['is_gp']:
+            model.k = k
+            model.time_k = k
+            m = min(model.neighbours(k), h.dataset_rows())
+            if m > 32:
+                raise Exception('nn > 32 neighbours is not supported by the warp-per-matrix GP kernel')
+            if starts is None:
+                starts = torch.from_numpy(model.draw_starts(N - I)).to(st['dev'])
+            st['starts'] = starts  # keep alive until the stream has consumed it
+            h.sweep(st['sys'], st['mG'], solver.h_mode, solver.Ng, st['t'], N, I, m, model.n_restarts, starts,
+                    model.fatol, model.xatol, st['u_next'], st['uG_next'], n, st['stream'])
+            model.train_count += (N - I) * n * N_JITTER * model.n_restarts
+        else:
+            for i in range(I, N):
+                h.rk_batch(st['sys'], st['mG'], solver.h_mode, solver.Ng, 1, st['t'][i:], st['t'][i + 1:],
+                           st['u_next'][i], n, st['uG_next'][i + 1], n, st['stream'])
+                torch.add(st['uF'][i + 1] - st['uG_cur'][i + 1], st['uG_next'][i + 1], out=st['u_next'][i + 1])
+
+    def device_errors(self, st):
+        """parareal.py:402: per-slice max-norm of u^{k+1}-u^k; the one device->host read of an iteration"""
+        st['h'].rowwise_maxabs_diff(st['u_next'], st['u_cur'], self.N + 1, self.n, st['err'], st['stream'])
+        return st['err'].cpu().numpy()
+
+    def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, max_rows=None, **kwargs):
+        import torch
+        if store_int:
+            raise NotImplementedError('intermediate checkpoints are outside the hot path')
+        N, eps = self.N, self.epsilon
+        verbose = kwargs.get('verbose', self.verbose)
         tic = time.time()
-        # coarse initialisation (parareal.py:264-277): N dependent one-slice launches
-        for i in range(N):
-            h.rk_batch(sysid, mG, solver.h_mode, solver.Ng, 1, d_t[i:], d_t[i + 1:], uG_cur[i], n, uG_cur[i + 1], n, stream)
-        u_cur.copy_(uG_cur)
-        u_next = u_cur.clone()
-        uG_next = uG_cur.clone()
-        torch.cuda.synchronize(dev)
-        G_time += time.time() - tic
-        I = 0
+        st = self.device_setup(model, max_rows=max_rows)
+        torch.cuda.synchronize(st['dev'])
+        G_time = time.time() - tic
+        F_time = sweep_time = 0.0
+        rank = st['rank']
         conv_int = []
         err = np.full((N + 1, N), np.nan)
         k = 0
@@ -272,66 +357,37 @@ class PararealDevice(Parareal):
             if verbose == 'v' and rank == 0:
                 print(f'{self.ode_name} {model.name} iteration number (out of {N}): {k+1} ')
             tic = time.time()
-            n_act = N - I
-            if world == 1:
-                h.rk_batch(sysid, mF, solver.h_mode, solver.Nf, n_act, d_t[I:], d_t[I + 1:], u_cur[I], n, uF[I + 1], n, stream)
-            else:
-                import torch.distributed as dist
-                chunk = (n_act + world - 1) // world
-                lo = min(I + rank * chunk, N)
-                cnt = max(0, min(chunk, N - lo))
-                if cnt > 0:
-                    h.rk_batch(sysid, mF, solver.h_mode, solver.Nf, cnt, d_t[lo:], d_t[lo + 1:], u_cur[lo], n, uF[lo + 1], n, stream)
-                view = uF[I + 1:I + 1 + world * chunk]
-                dist.all_gather_into_tensor(view, view[rank * chunk:(rank + 1) * chunk], group=self.group)
-            if self.events is not None:
-                torch.cuda.synchronize(dev)
-                F_time += time.time() - tic
-            # slice I+1 is exact (parareal.py:331-334)
-            u_next[I + 1].copy_(uF[I + 1])
-            uG_next[I + 1].copy_(uG_cur[I + 1])
-            I += 1
-            if is_gp:
-                h.append_iteration(u_cur, uF, uG_cur, N, I, n, stream)
-                model._n_dev = h.dataset_rows()
-            if I == N:
-                h.rowwise_maxabs_diff(u_next, u_cur, N + 1, n, d_err, stream)
-                err[:, k] = d_err.cpu().numpy()
-                err[-1, k] = np.nextafter(eps, 0)
-                u_cur.copy_(u_next)
-                break
+            self.device_fine_step(st)
+            torch.cuda.synchronize(st['dev'])
+            F_time += time.time() - tic
             tic = time.time()
-            if is_gp:
-                model.k = k
-                model.time_k = k
-                m = min(model.neighbours(k), h.dataset_rows())
-                starts = torch.from_numpy(model.draw_starts(N - I)).to(dev)
-                h.sweep(sysid, mG, solver.h_mode, solver.Ng, d_t, N, I, m, model.n_restarts, starts,
-                        model.fatol, model.xatol, u_next, uG_next, n, stream)
-                model.train_count += (N - I) * n * N_JITTER * model.n_restarts
-            else:
-                for i in range(I, N):
-                    h.rk_batch(sysid, mG, solver.h_mode, solver.Ng, 1, d_t[i:], d_t[i + 1:], u_next[i], n, uG_next[i + 1], n, stream)
-                    torch.add(uF[i + 1] - uG_cur[i + 1], uG_next[i + 1], out=u_next[i + 1])
-            # convergence bookkeeping (parareal.py:396-416): one device->host read per iteration
-            h.rowwise_maxabs_diff(u_next, u_cur, N + 1, n, d_err, stream)
-            err[:, k] = d_err.cpu().numpy()
+            self.device_sweep(st, k)
+            I = st['I']
+            if I == N:
+                if verbose == 'v' and rank == 0:
+                    print('WARNING: early stopping')
+                err[:, k] = self.device_errors(st)
+                err[-1, k] = np.nextafter(eps, 0)
+                st['u_cur'].copy_(st['u_next'])
+                break
+            err[:, k] = self.device_errors(st)
             dt_sweep = time.time() - tic
             sweep_time += dt_sweep
-            if is_gp:
+            if st['is_gp']:
                 model.pred_time += dt_sweep
                 model.pred_times[k] += dt_sweep
                 model.tot_train_t += dt_sweep
-            if np.any(np.isnan(err[:, k])) and bool(torch.isnan(uG_next).any()):
+            if np.any(np.isnan(err[:, k])) and bool(torch.isnan(st['uG_next']).any()):
                 raise Exception("NaN values in initial coarse solve - increase Ng!")
             err[I, k] = 0
-            u_cur.copy_(u_next)
-            uG_cur.copy_(uG_next)
-            for p in range(I + 1, N + 1):
+            st['u_cur'].copy_(st['u_next'])
+            st['uG_cur'].copy_(st['uG_next'])
+            for p in range(I + 1, N + 1):  # parareal.py:408-416
                 if err[p, k] < eps:
                     I += 1
                 else:
                     break
+            st['I'] = I
             if verbose == 'v' and rank == 0:
                 print('--> Converged:', I)
             conv_int.append(I)
@@ -341,10 +397,9 @@ class PararealDevice(Parareal):
                 break
         timings = {'F_time': F_time, 'G_time': G_time, 'F_time_serial_avg': F_time / max(N, 1), 'sweep_time': sweep_time}
         timings.update(model.get_times())
-        out = {'t': t_host, 'u': u_cur.cpu().numpy(), 'err': err[:, :k + 1], 'k': k + 1, 'timings': timings,
-               'debug_dict': {}, 'converged': I == N, 'conv_int': conv_int}
-        out['u_last'] = out['u']
-        if is_gp and return_data:
-            rows = h.dataset_rows()
-            out['n_rows'] = rows
+        u = st['u_cur'].cpu().numpy()
+        out = {'t': st['t_host'], 'u': u, 'u_last': u, 'err': err[:, :k + 1], 'k': k + 1, 'timings': timings,
+               'debug_dict': {}, 'converged': st['I'] == N, 'conv_int': conv_int}
+        if st['is_gp']:
+            out['n_rows'] = st['h'].dataset_rows()
         return out

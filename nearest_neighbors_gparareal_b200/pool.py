@@ -19,6 +19,30 @@ class MyPool():
 
 
 class CudaPool():
+    """sharded=True (with an initialised torch.distributed NCCL group of W ranks, one per GPU): each
+    rank propagates a contiguous block of the slices and the blocks are exchanged with ONE
+    all-gather -- the multi-GPU analogue of the reference's MPIPoolExecutor (FHN_PDE.py:123-126)."""
+
+    def __init__(self, sharded=False, group=None):
+        self.sharded = sharded
+        self.group = group
+
+    def _batch(self, batch, t0, t1, u0):
+        if self.sharded:
+            import torch
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+                n, d = u0.shape
+                chunk = (n + world - 1) // world
+                lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+                buf = torch.zeros((world * chunk, d), dtype=torch.float64, device='cuda')
+                if hi > lo:
+                    buf[lo:hi] = torch.from_numpy(batch(t0[lo:hi], t1[lo:hi], u0[lo:hi])).cuda()
+                dist.all_gather_into_tensor(buf, buf[rank * chunk:(rank + 1) * chunk], group=self.group)
+                return buf[:n].cpu().numpy()
+        return batch(t0, t1, u0)
+
     def map(self, fn, *iterables, chunksize=None):
         owner = getattr(fn, "__self__", None)
         name = getattr(fn, "__name__", "")
@@ -29,7 +53,7 @@ class CudaPool():
                 return []
             s = time.time()
             batch = owner.run_F_batch if "F" in name else owner.run_G_batch
-            u1 = batch(np.asarray(t0, dtype=float), np.asarray(t1, dtype=float), np.stack(u0))
+            u1 = self._batch(batch, np.asarray(t0, dtype=float), np.asarray(t1, dtype=float), np.stack(u0))
             secs = (time.time() - s) / len(t0)
             if name.endswith("_timed"):
                 return [(u1[i], secs) for i in range(len(t0))]

@@ -1,0 +1,86 @@
+"""GPU: end-to-end nnGParareal runs through the reference-facing Python surface -- same convergence
+iteration count K / conv_int as the unmodified reference (golden runs) and final trajectory inside the
+Parareal tolerance; the device-resident driver equals the host-protocol driver bit for bit."""
+import numpy as np
+import pytest
+
+import nearest_neighbors_gparareal_b200 as nn
+from helpers import load_run, case_system, device_system
+
+pytestmark = pytest.mark.gpu
+
+
+def build(name, driver):
+    z, cfg, mkw = load_run(name)
+    key, kw = case_system(name)
+    ode = device_system(key, **kw)
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **{k: cfg[k] for k in ("Ng", "Nf", "F", "G")})
+    p = driver(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=float(z["epsilon"]), verbose='')
+    return z, cfg, mkw, p
+
+
+# name -> (K must equal the reference's, conv_int must equal the reference's)
+# Lorenz is chaotic and Hopf N=32 is borderline (the reference's own K is 9,10,10,10,10 over seeds
+# 45..49, `NNGP_all_but_pend`): there the tie-breaking noise of the reference moves conv_int.
+CASES = {"lorenz_N32_m11": (True, True), "lorenz_N50_m11": (True, False), "lorenz_N50_adaptive": (True, False),
+         "hopf_N32_m15": (False, False), "burgers_d32_N32_m12": (True, True), "fhn_d32_N32_m12": (True, True)}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_same_K_and_trajectory_as_reference(name):
+    z, cfg, mkw, p = build(name, nn.PararealDevice)
+    out = p.run(model='nngp', **mkw)
+    eps = float(z["epsilon"])
+    same_K, same_conv = CASES[name]
+    assert out['converged']
+    K_ref = int(z["K"])
+    assert abs(out['k'] - K_ref) <= (0 if same_K else 1), (out['conv_int'], list(z["conv_int"]))
+    if same_conv:
+        assert out['conv_int'] == [int(v) for v in z["conv_int"]]
+    # accuracy against the serial fine solution: as good as the reference's own final iterate
+    N = cfg["N"]
+    fine = np.zeros_like(out['u'])
+    fine[0] = p.u0
+    for i in range(N):
+        fine[i + 1] = p.solver.run_F(out['t'][i], out['t'][i + 1], fine[i])
+    acc = np.max(np.abs(out['u'] - fine))
+    acc_ref = np.max(np.abs(z["u_last"] - fine))
+    assert acc <= max(eps, 3 * acc_ref), (acc, acc_ref)
+    if same_conv:
+        # final trajectory inside the Parareal tolerance of the reference's (up to the chaos amplification
+        # the reference's own iterate shows against the fine solution)
+        assert np.max(np.abs(out['u'] - z["u_last"])) <= max(eps, 2 * acc_ref)
+        np.testing.assert_allclose(np.nanmax(out['err'], axis=0)[:2], np.nanmax(z["err"], axis=0)[:2], rtol=5e-2)
+    # the first iteration's errors come from identical data (F and G are exact): same order of magnitude
+    assert abs(np.log10(np.nanmax(out['err'][:, 0]) / np.nanmax(z["err"][:, 0]))) < 0.05
+
+
+@pytest.mark.parametrize("name", ["lorenz_N32_m11", "fhn_d32_N32_m12"])
+def test_device_driver_equals_host_protocol_driver(name):
+    """PararealDevice (fused on-device sweep) == Parareal (reference loop over solver/model/pool protocols)"""
+    z, cfg, mkw, pd = build(name, nn.PararealDevice)
+    od = pd.run(model='nngp', **mkw)
+    z, cfg, mkw, ph = build(name, nn.Parareal)
+    oh = ph.run(model='nngp', pool=nn.CudaPool(), parall='mpi', **mkw)
+    assert od['k'] == oh['k'] and od['conv_int'] == oh['conv_int']
+    assert np.array_equal(od['u'], oh['u_last'])
+    assert np.array_equal(od['err'], oh['err'], equal_nan=True)
+    assert oh['u'].shape == (cfg["N"] + 1, oh['u_last'].shape[1], oh['k'])
+    for key in ('F_time', 'G_time', 'F_time_serial_avg', 'mdl_train_t', 'mdl_pred_t', 'mdl_tot_t', 'by_iter',
+                'serial_train_time', 'avg_serial_train_time', 'runtime'):
+        assert key in oh['timings'], key
+    # serial F loop (parall='Serial', per-slice launches) gives the same numbers as the batched launch
+    z, cfg, mkw, ps = build(name, nn.PararealLight)
+    os_ = ps.run(model='nngp', early_stop=2, **mkw)
+    assert np.array_equal(os_['err'][:, :2], oh['err'][:, :2], equal_nan=True)
+
+
+def test_plain_parareal_matches_published_K():
+    """BareParareal through both drivers: Lorenz preset -> K=15 (Table 2 of the reference, `all_models`)"""
+    ode = nn.Lorenz(normalization='-11')
+    cfg = nn.Config(ode).get()
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+    out = nn.PararealDevice(ode, solver, verbose='', **cfg).run(model='parareal')
+    assert out['k'] == 15 and out['conv_int'] == [1, 2, 3, 5, 8, 14, 17, 20, 26, 30, 33, 37, 40, 43, 50]
+    out2 = nn.Parareal(ode, solver, verbose='', **cfg).run(model='parareal', pool=nn.CudaPool(), parall='mpi')
+    assert out2['k'] == 15 and np.array_equal(out2['u_last'], out['u'])

@@ -1,0 +1,319 @@
+"""GPU: kernel-level parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors recorded from the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import nearest_neighbors_gparareal_b200 as nn
+from nearest_neighbors_gparareal_b200 import _lib
+from oracle import nngp as onn
+from oracle import rk as ork
+from oracle import systems as osys
+from helpers import GOLDEN, load_run, samples
+
+pytestmark = pytest.mark.gpu
+
+BITWISE = ["lorenz", "lorenz_id", "hopf", "rossler", "fhn_ode", "brusselator"]  # closed form, no libm calls
+TOLERANT = {"dblpend": 1e-14, "thomas": 1e-14, "burgers128": 1e-11, "burgers32": 1e-11, "fhn16": 1e-11,
+            "fhn4": 1e-12, "fhn4_n": 1e-12}
+DEV = {"lorenz": lambda: nn.Lorenz(normalization='-11'), "lorenz_id": lambda: nn.Lorenz(),
+       "hopf": lambda: nn.Hopf(normalization='-11'), "rossler": lambda: nn.Rossler(normalization='-11'),
+       "fhn_ode": lambda: nn.FHN_ODE(normalization='-11'), "brusselator": lambda: nn.Brusselator(normalization='-11'),
+       "dblpend": lambda: nn.DblPend(normalization='-11'), "thomas": lambda: nn.ThomasLabyrinth(normalization='-11'),
+       "burgers128": lambda: nn.Burgers(d_x=128, normalization='-11'),
+       "burgers32": lambda: nn.Burgers(d_x=32, normalization='-11'),
+       "fhn16": lambda: nn.FHN_PDE(d_x=16), "fhn4": lambda: nn.FHN_PDE(d_x=4),
+       "fhn4_n": lambda: nn.FHN_PDE(d_x=4, normalization='-11')}
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-300)))
+
+
+def scaled_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def rkv():
+    return np.load(os.path.join(GOLDEN, "rk_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(DEV))
+def test_rk_and_vector_field_vs_reference_vectors(rkv, name):
+    """device RHS + RK == reference systems.py/RK.py outputs: bit-exact for the closed-form ODEs,
+    1e-11 (scaled) for the stencil form of the dense PDE operators and the libm-dependent fields"""
+    ode = DEV[name]()
+    f = ode.get_vector_field()
+    U = rkv[f"{name}_u"]
+    got = f(0.3, U)
+    if name in BITWISE:
+        assert np.array_equal(got, rkv[f"{name}_f"])
+    else:
+        assert scaled_err(got, rkv[f"{name}_f"]) < TOLERANT[name]
+    assert np.array_equal(f(0.0, U[1]), got[1])  # single vector call, t ignored (autonomous)
+    for method in ("RK1", "RK2", "RK4", "RK8"):
+        t0, t1, steps = rkv[f"{name}_{method}_t"]
+        s = nn.CudaSolverRK(f, Ng=int(steps), Nf=int(steps), F=method, G=method)
+        got = s.run_F_batch([t0] * 3, [t1] * 3, U[:3])
+        want = rkv[f"{name}_{method}_u1"]
+        if name in BITWISE:
+            assert np.array_equal(got, want), method
+        else:
+            assert scaled_err(got, want) < TOLERANT[name], method
+        assert np.array_equal(s.run_G(t0, t1, U[2]), got[2])  # one-slice call == batched call
+
+
+def test_rk_many_slices_both_step_conventions_vs_oracle():
+    rng = np.random.default_rng(5)
+    o = osys.Lorenz(normalization='-11')
+    ode = nn.Lorenz(normalization='-11')
+    n = 70  # more than two warps of slices, ragged last block
+    u0 = o.u0[None, :] + 0.05 * rng.standard_normal((n, 3))
+    t0 = np.linspace(0, 3, n)
+    t1 = t0 + rng.uniform(0.05, 0.3, n)
+    for h_mode in ("linspace", "const"):
+        s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=37, F='RK8', G='RK4', h_mode=h_mode)
+        got = s.run_F_batch(t0, t1, u0)
+        want = np.stack([ork.rk_last(o.f, 'RK8', t0[i], t1[i], 37, u0[i], h_mode) for i in range(n)])
+        assert np.array_equal(got, want), h_mode
+    o2, d2 = osys.FHN_PDE(d_x=6), nn.FHN_PDE(d_x=6)
+    u0 = o2.u0[None, :] + 0.01 * rng.standard_normal((9, 72))
+    s = nn.CudaSolverRK(d2.get_vector_field(), Ng=5, Nf=20, F='RK8', G='RK2')
+    got = s.run_F_batch(np.arange(9.0), np.arange(9.0) + 2.0, u0)
+    want = np.stack([ork.rk_last(o2.f, 'RK8', float(i), i + 2.0, 20, u0[i]) for i in range(9)])
+    assert scaled_err(got, want) < 1e-12
+    got = s.run_G_batch(np.arange(9.0), np.arange(9.0) + 2.0, u0)
+    want = np.stack([ork.rk_last(o2.f, 'RK2', float(i), i + 2.0, 5, u0[i]) for i in range(9)])
+    assert scaled_err(got, want) < 1e-12
+    # paging quirk of solver.py:89-96 (steps > thresh): every page runs with the total step count
+    sp = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=25, F='RK4', G='RK4', thresh=10)
+    u = o.u0.copy()
+    st = 24
+    step = (0.5 - 0.0) / st
+    ta = 0.0
+    for page in (10, 10, 4):
+        tb = ta + step * page
+        u = ork.rk_last(o.f, 'RK4', ta, tb, st, u)
+        ta = tb
+    assert np.array_equal(sp.run_F(0.0, 0.5, o.u0), u)
+
+
+def test_rk_errors(handle):
+    ode = nn.Burgers(d_x=2000, normalization='-11')
+    s = nn.CudaSolverRK(ode.get_vector_field(), Ng=1, Nf=1, F='RK4', G='RK1')
+    with pytest.raises(_lib.NNGPError, match="outside"):
+        s.run_G(0.0, 1.0, ode.get_init_cond())
+    ode = nn.Lorenz()
+    s = nn.CudaSolverRK(ode.get_vector_field(), Ng=0, Nf=1, F='RK4', G='RK1')
+    with pytest.raises(_lib.NNGPError, match="steps must be >= 1"):
+        s.run_G(0.0, 1.0, ode.get_init_cond())
+
+
+def make_dataset(rng, n, d):
+    x = rng.uniform(-1, 1, (n, d))
+    y = 1e-3 * np.sin(x @ (rng.standard_normal((d, d)) / np.sqrt(d)))
+    return x, y
+
+
+@pytest.mark.parametrize("n,d,m,nq", [(40, 3, 11, 1), (300, 3, 11, 5), (2000, 32, 12, 9), (3055, 512, 20, 1),
+                                       (3055, 512, 20, 12), (5000, 128, 30, 33), (65, 7, 32, 3), (20, 2, 20, 2),
+                                       (700, 1100, 5, 6)])
+def test_knn_bit_exact(handle, n, d, m, nq):
+    """index sets AND squared distances bit-identical to argsort(cdist(q, x, 'sqeuclidean'))[:m]"""
+    rng = np.random.default_rng(n + d)
+    x, y = make_dataset(rng, n, d)
+    Q = x[rng.permutation(n)[:nq]] + 1e-3 * rng.standard_normal((nq, d))
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x[:n // 2], y[:n // 2])
+    handle.dataset_append_host(x[n // 2:], y[n // 2:])  # appended in two pieces like two iterations
+    assert handle.dataset_rows() == n
+    idx, dist = handle.knn_host(Q, m)
+    for qi in range(nq):
+        oi, od = onn.knn(Q[qi], x, m)
+        assert np.array_equal(idx[qi], oi) and np.array_equal(dist[qi], od)
+    if n > 2 * m:  # prefix search: only the first rows (what a predict at an earlier iteration sees)
+        idx, dist = handle.knn_host(Q[:1], m, n_rows=n // 2)
+        oi, od = onn.knn(Q[0], x[:n // 2], m)
+        assert np.array_equal(idx[0], oi) and np.array_equal(dist[0], od)
+
+
+def test_knn_ties_broken_by_index_and_edge_cases(handle):
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((30, 4))
+    x = np.concatenate([base, base, base[:10]])  # exact duplicates -> exact distance ties
+    y = np.zeros_like(x)
+    handle.dataset_reset()
+    handle.dataset_reserve(200, 4)
+    handle.dataset_append_host(x, y)
+    q = base[3] + 1e-4
+    idx, dist = handle.knn_host(q[None], 9)
+    oi, od = onn.knn(q, x, 9)
+    assert np.array_equal(idx[0], oi) and np.array_equal(dist[0], od)
+    assert list(idx[0][:3]) == [3, 33, 63]  # same distance, ascending index
+    # query equal to a dataset row: distance exactly 0 first
+    idx, dist = handle.knn_host(base[5][None], 3)
+    assert dist[0, 0] == 0.0 and idx[0, 0] == 5
+    with pytest.raises(_lib.NNGPError, match="outside"):
+        handle.knn_host(q[None], 33)
+    with pytest.raises(_lib.NNGPError, match="fewer than m"):
+        handle.knn_host(q[None], 9, n_rows=5)
+    handle.dataset_reset()
+    assert handle.dataset_rows() == 0
+    with pytest.raises(_lib.NNGPError):
+        handle.knn_host(q[None], 3)
+
+
+def _gp_problem(handle, rng, n, d, m, nq, near=1e-3):
+    import torch
+    x, y = make_dataset(rng, n, d)
+    Q = x[rng.permutation(n)[:nq]] + near * rng.standard_normal((nq, d))
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    idx, dist = handle.knn_host(Q, m)
+    dev = torch.device('cuda', handle.device)
+    return x, y, Q, idx, dist, dev
+
+
+@pytest.mark.parametrize("n,d,m", [(300, 3, 11), (500, 6, 5), (800, 16, 20), (400, 8, 30), (900, 4, 17)])
+def test_objective_parity(handle, n, d, m):
+    """nll(theta) == models.py:240-252 within 1e-9 relative on well-conditioned points, and +inf exactly
+    where the reference returns inf (failed factorisation / NaN)"""
+    import torch
+    rng = np.random.default_rng(7 + m)
+    nq, nt = 3, 40
+    x, y, Q, idx, dist, dev = _gp_problem(handle, rng, n, d, m, nq)
+    theta = np.stack([rng.uniform(-9, 2, (nq, d, nt)), rng.uniform(-9, 0, (nq, d, nt))], axis=-1)
+    theta[:, :, 0] = [-400.0, -3.0]   # 10**sx underflows -> 1/0 = inf -> NaN -> +inf
+    theta[:, :, 1] = [4.0, -2.0]      # huge length scale: singular kernel matrix
+    theta[:, :, 2] = [-3.0, 400.0]    # amplitude overflows
+    jit = rng.integers(-20, -11, (nq, d, nt)).astype(float)
+    t_idx = torch.from_numpy(idx).to(dev)
+    t_th = torch.from_numpy(theta).to(dev)
+    t_j10 = torch.from_numpy(10.0 ** 0 * np.array([[[10 ** j for j in row] for row in blk] for blk in jit])).to(dev)
+    out = torch.empty((nq, d, nt), dtype=torch.float64, device=dev)
+    handle.gp_nll(t_idx, nq, m, nt, t_th, t_j10, out)
+    got = out.cpu().numpy()
+    n_inf = n_cmp = 0
+    for qi in range(nq):
+        r2 = onn.pairwise_sqdist(x[idx[qi]], x[idx[qi]])
+        for j in range(d):
+            yy = y[idx[qi], j]
+            for t in range(nt):
+                want = onn.neg_log_lik(r2, yy, theta[qi, j, t], jit[qi, j, t])
+                g = got[qi, j, t]
+                if not np.isfinite(want):
+                    n_inf += 1
+                    # a singular matrix may fail in one factorisation and squeak through in the other
+                    assert np.isinf(g) or t == 1, (theta[qi, j, t], want, g)
+                    continue
+                K = onn.se_kernel_from_r2(r2, theta[qi, j, t]) + np.eye(m) * 10 ** jit[qi, j, t]
+                cond = np.linalg.cond(K)
+                if cond < 1e6:
+                    n_cmp += 1
+                    assert abs(g - want) <= 1e-9 * max(1.0, abs(want)), (theta[qi, j, t], cond, want, g)
+    assert n_inf >= 2 * nq * d and n_cmp > nq * d * 5
+
+
+@pytest.mark.parametrize("n,d,m", [(300, 3, 11), (800, 16, 20), (400, 8, 30), (600, 5, 13)])
+def test_prediction_given_identical_hyperparameters(handle, n, d, m):
+    """north_star: GP predictions within 1e-8 relative given identical hyper-parameters"""
+    import torch
+    rng = np.random.default_rng(11 + m)
+    nq = 4
+    x, y, Q, idx, dist, dev = _gp_problem(handle, rng, n, d, m, nq)
+    theta = np.stack([rng.uniform(-2.5, 0.5, (nq, d)), rng.uniform(-8, -1, (nq, d))], axis=-1)
+    jit = rng.integers(-20, -11, (nq, d)).astype(float)
+    pred = torch.empty((nq, d), dtype=torch.float64, device=dev)
+    handle.gp_mean(torch.from_numpy(Q).to(dev), torch.from_numpy(idx).to(dev), torch.from_numpy(dist).to(dev),
+                   nq, m, torch.from_numpy(theta).to(dev), torch.from_numpy(jit).to(dev), pred)
+    got = pred.cpu().numpy()
+    worst = 0.0
+    for qi in range(nq):
+        r2 = onn.pairwise_sqdist(x[idx[qi]], x[idx[qi]])
+        for j in range(d):
+            want = onn.posterior_mean(r2, dist[qi], y[idx[qi], j], theta[qi, j], jit[qi, j])
+            K = onn.se_kernel_from_r2(r2, theta[qi, j]) + np.eye(m) * 10 ** jit[qi, j]
+            if np.linalg.cond(K) < 1e7:
+                worst = max(worst, abs(got[qi, j] - want) / abs(want))
+    assert worst < 1e-8, worst
+
+
+@pytest.mark.parametrize("n,d,m,R", [(300, 3, 11, 1), (600, 6, 15, 2), (800, 12, 20, 1), (300, 4, 30, 1)])
+def test_fit_predict_vs_oracle(handle, n, d, m, R):
+    """full predict (kNN + 9R Nelder-Mead fits per dimension + selection + mean) against the oracle on
+    the same host-drawn starts"""
+    rng = np.random.default_rng(100 + m)
+    x, y = make_dataset(rng, n, d)
+    q = x[3] + 1e-3 * rng.standard_normal(d)
+    model = nn.CudaNNGP(n=d, N=4, nn=m, seed=45, n_restarts=R, handle=handle)
+    model.fit(x, y, k=0)
+    state = model.rng.bit_generator.state
+    pred, det = model.predict(q.reshape(1, -1), None, None, i=0, return_details=True)
+    orng = np.random.default_rng()
+    orng.bit_generator.state = state
+    starts = onn.draw_starts(orng, d, R)
+    opred, odet = onn.predict(q, x, y, m, starts, return_details=True)
+    assert np.array_equal(det['idx'][0], odet['idx'])
+    same = 0
+    for j in range(d):
+        for a in range(9):
+            for r in range(R):
+                same += bool(np.array_equal(det['thetas'][0, j, a, r], odet['thetas'][j, a, r])
+                             and det['nfev'][0, j, a, r] == odet['nfev'][j, a, r])
+    frac = same / (d * 9 * R)
+    assert frac > 0.5, f"only {frac:.2f} of the Nelder-Mead runs follow the SciPy trajectory exactly"
+    # every run ends at (numerically) the same objective value as the reference search or better/equal basin
+    finite = np.isfinite(odet['fvals']) & np.isfinite(det['fvals'][0])
+    assert np.median(np.abs(det['fvals'][0][finite] - odet['fvals'][finite])) < 1e-6
+    # the device's own selection is the reference rule applied to its own fvals
+    for j in range(d):
+        best = onn.select(det['fvals'][0, j])
+        a, r = divmod(best, R)
+        assert det['jitter_opt'][0, j] == -20 + a
+        assert np.array_equal(det['theta_opt'][0, j], det['thetas'][0, j, a, r])
+        assert det['fval_opt'][0, j] == det['fvals'][0, j, a, r]
+        want = onn.posterior_mean(odet['r2'], odet['dist'], y[odet['idx'], j], det['theta_opt'][0, j], det['jitter_opt'][0, j])
+        assert abs(pred[j] - want) <= 1e-8 * abs(want) + 1e-16
+    assert np.all(det['nfev'] >= 3) and np.all(det['nfev'] <= 400)
+    np.testing.assert_allclose(det['fval_opt'][0], odet['fval_opt'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["lorenz_N50_m11", "hopf_N32_m15", "burgers_d32_N32_m12", "fhn_d32_N32_m12"])
+def test_predict_on_reference_run_samples(handle, name):
+    """device predict on (query, dataset prefix, starts) recorded inside a run of the unmodified
+    reference.  The neighbour sets are the reference's.  The reference's selection among its 9R
+    searches is decided by the last bits of fval whenever several searches end in the same flat valley
+    of the likelihood ("ties"), so the check is: the device finds an optimum as good as the
+    reference's, and its prediction is the reference's posterior mean at the device's hyper-parameters."""
+    z, cfg, mkw = load_run(name)
+    x, D = z["x"], z["D"]
+    d = x.shape[1]
+    handle.dataset_reset()
+    handle.dataset_reserve(x.shape[0], d)
+    handle.dataset_append_host(x, D)
+    as_good = total = same_pred = 0
+    for s in samples(z)[:4 if d > 8 else 8]:
+        n = int(s["n_rows"])
+        m = int(s["m"])
+        R = s["starts"].shape[2]
+        out = handle.predict_host(s["query"][None], m, s["starts"][None], R, 0.1, 0.1, n_rows=n, details=True)
+        oi, okq = onn.knn(s["query"], x[:n], m)
+        assert np.array_equal(out["idx"][0], oi)
+        r2 = onn.pairwise_sqdist(x[oi], x[oi])
+        dims = range(d) if d <= 8 else range(0, d, 5)
+        for j in dims:
+            yj = D[oi, j]
+            ref_f = min(onn.nm_run(r2, yj, s["starts"][j, a, r].astype(float), onn.JITTERS[a], 0.1, 0.1)[1]
+                        for a in range(9) for r in range(R))
+            g_f = out["fval_opt"][0, j]
+            total += 1
+            as_good += bool(g_f <= ref_f + 1e-8 * max(1.0, abs(ref_f)))
+            want = onn.posterior_mean(r2, okq, yj, out["theta_opt"][0, j], out["jitter_opt"][0, j])
+            assert abs(out["pred"][0, j] - want) <= 1e-7 * abs(want) + 1e-14, (j, out["pred"][0, j], want)
+            same_pred += bool(abs(out["pred"][0, j] - s["preds"][j]) <= 1e-8 * abs(s["preds"][j]) + 1e-13)
+    assert as_good >= 0.9 * total, (as_good, total)
+    print(f"{name}: optimum as good as the reference's in {as_good}/{total}, identical prediction in {same_pred}/{total}")

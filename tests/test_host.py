@@ -1,0 +1,191 @@
+"""CPU: host-side logic and the C-ABI boundary (no compute calls: there is no GPU here)."""
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import nearest_neighbors_gparareal_b200 as nn
+from nearest_neighbors_gparareal_b200 import _lib, parareal as ppara
+from oracle import systems as osys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "nngpara.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nngp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        from nearest_neighbors_gparareal_b200.build import build
+        build()
+    lib = _lib.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for name in syms:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.nngp_abi_version() == 1
+
+
+def test_tableau_equals_reference_tableau():
+    """the Butcher tableaus compiled into the library == RK.py:30-48 (oracle restatement), bit for bit"""
+    import ctypes
+    from oracle import rk as ork
+    lib = _lib.load_library()
+    for name, code in _lib.METHODS.items():
+        S = ctypes.c_int(0)
+        a, b, c = np.zeros(121), np.zeros(11), np.zeros(11)
+        assert lib.nngp_get_tableau(code, ctypes.byref(S), a.ctypes.data, b.ctypes.data, c.ctypes.data) == 0
+        s = S.value
+        oa, ob, oc = ork.tableau(name)
+        assert np.array_equal(a[:s * s].reshape(s, s), oa) and np.array_equal(b[:s], ob) and np.array_equal(c[:s], oc)
+    assert lib.nngp_get_tableau(3, ctypes.byref(S), a.ctypes.data, b.ctypes.data, c.ctypes.data) != 0
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.NNGPError, match="no CPU fallback|no CUDA device"):
+        _lib.Handle(0)
+
+
+def test_start_points_stream_is_the_reference_stream():
+    """models.py:192 draws rng.integers(-8,0,2) once per task; the vectorised draw is identical"""
+    m = nn.CudaNNGP(n=5, N=8, nn=11, seed=45, n_restarts=2)
+    ref = np.random.default_rng(45)
+    want = np.stack([ref.integers(-8, 0, 2) for _ in range(3 * 5 * 9 * 2)]).reshape(3, 5, 9, 2, 2)
+    got = np.concatenate([m.draw_starts(1), m.draw_starts(2)])
+    assert got.dtype == np.int8 and np.array_equal(got, want)
+    assert got.min() >= -8 and got.max() <= -1
+    assert m.neighbours(0) == 11
+    assert nn.CudaNNGP(n=5, N=8).neighbours(0) == 10 and nn.CudaNNGP(n=5, N=8).neighbours(20) == 22
+
+
+def test_systems_mirror_reference_initial_conditions_and_presets():
+    pairs = [(nn.Lorenz(normalization='-11'), osys.Lorenz(normalization='-11')),
+             (nn.Hopf(normalization='-11'), osys.Hopf(normalization='-11')),
+             (nn.Burgers(d_x=128, normalization='-11'), osys.Burgers(d_x=128, normalization='-11')),
+             (nn.FHN_PDE(d_x=16), osys.FHN_PDE(d_x=16)), (nn.Rossler(), osys.Rossler())]
+    for dev, ora in pairs:
+        assert np.array_equal(dev.get_init_cond(), ora.u0), dev.name
+        assert dev.name == ora.name and dev.get_dim() == ora.dim()
+    for dev, ora, N in [(nn.Lorenz(normalization='-11'), osys.Lorenz(normalization='-11'), None),
+                        (nn.Hopf(normalization='-11'), osys.Hopf(normalization='-11'), 64),
+                        (nn.FHN_PDE(d_x=16), osys.FHN_PDE(d_x=16), None), (nn.Brusselator(), osys.Brusselator(), None)]:
+        got = nn.Config(dev, N=N, d_x=getattr(dev, 'd_x', None)).get()
+        want = osys.preset(ora, N=N)
+        assert {k: got[k] for k in want} == want
+    assert nn.Hopf(normalization='-11').name == 'Hopf'
+    h = nn.Hopf(normalization='-11')
+    nn.Config(h, N=32)
+    assert h.name == 'Hopf_32'  # configs.py:149
+    # FHN stencil coefficients == entries of the reference's dense a*(DXX+DYY), b*(DXX+DYY)
+    o = osys.FHN_PDE(d_x=16)
+    A = 2.8e-4 * (o.DXX + o.DYY)
+    B = 5e-3 * (o.DXX + o.DYY)
+    p = nn.FHN_PDE(d_x=16).device_params()
+    assert p[0] == 16 and p[1] == A[0, 0] and p[2] == A[0, 1] == A[0, 16] == A[0, 15] and p[3] == B[5, 5] and p[4] == B[5, 6]
+    assert np.count_nonzero(A[7]) == 5
+    ob = osys.Burgers(d_x=32, normalization='-11')
+    pb = nn.Burgers(d_x=32, normalization='-11').device_params()
+    assert pb[0] == ob.Dxx[3, 4] == ob.Dxx[0, 31] and pb[1] == ob.Dxx[3, 3] and pb[2] == ob.Dx[3, 4] == -ob.Dx[3, 2] == -ob.Dx[0, 31]
+
+
+def test_protocol_errors_match_reference():
+    ode = nn.Lorenz(normalization='-11')
+    with pytest.raises(Exception, match='ode must be an instance of the ODE class'):
+        nn.Parareal(object(), None, [0, 1], 4)
+    with pytest.raises(Exception, match='solver must be an instance of the SolverAbstr class'):
+        nn.Parareal(ode, object(), [0, 1], 4)
+    with pytest.raises(NotImplementedError, match='Only RK1, RK2, RK4 and RK8'):
+        nn.CudaSolverRK(ode.get_vector_field(), 4, 8, 'RK3', 'RK1')
+    with pytest.raises(NotImplementedError, match='Only identity and -11'):
+        nn.Lorenz(normalization='01')
+    with pytest.raises(Exception, match='no CPU fallback'):
+        nn.CudaSolverRK(lambda t, u: u, 4, 8, 'RK4', 'RK1')
+    s = nn.CudaSolverRK(ode.get_vector_field(), Ng=4, Nf=8, F='RK4', G='RK1', extra_key_is_swallowed=1)
+    p = nn.Parareal(ode, s, tspan=[0, 1], N=4, Ng=4, Nf=8, F='RK4', G='RK1')
+    with pytest.raises(Exception, match='Not implemented'):
+        p._make_model('gpjax', pool=None)
+    s2 = pickle.loads(pickle.dumps(s))
+    assert s2.Nf == 8 and s2.ode.name == 'Lorenz'
+
+
+def test_cuda_pool_batches_solver_calls():
+    class Fake:
+        def __init__(self):
+            self.calls = 0
+
+        def run_F_batch(self, t0, t1, u0):
+            self.calls += 1
+            return u0 + (t1 - t0)[:, None]
+
+        def run_F_timed(self, t0, t1, u0):
+            raise AssertionError("must be batched")
+
+    f = Fake()
+    pool = nn.CudaPool()
+    u0 = [np.zeros(3), np.ones(3), 2 * np.ones(3)]
+    out = list(pool.map(f.run_F_timed, [0, 1, 2], [1, 3, 5], u0))
+    assert f.calls == 1 and len(out) == 3
+    assert np.array_equal(out[2][0], 2 * np.ones(3) + 3) and out[0][1] >= 0
+    assert list(pool.map(lambda a, b: a + b, [1, 2], [3, 4])) == [4, 6]
+    assert list(nn.MyPool.map(lambda a: a * 2, [1, 2], chunksize=4)) == [2, 4]
+
+
+def test_slice_block_partition_covers_all_slices():
+    for N in (5, 32, 512):
+        for I in (0, 1, 7, N - 1):
+            if I >= N:
+                continue
+            for world in (1, 2, 3, 8):
+                owned = []
+                for r in range(world):
+                    chunk, lo, cnt = ppara.slice_block(I, N, r, world)
+                    assert lo == min(I + r * chunk, N)
+                    owned += list(range(lo, lo + cnt))
+                assert owned == list(range(I, N))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from nearest_neighbors_gparareal_b200.parareal import slice_block, gather_fine_rows
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[4])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+N, d = 13, 5
+ok = True
+for I in (0, 1, 4, 12):
+    uF = torch.full((N + 1 + N + world, d), -1.0, dtype=torch.float64)
+    keep = torch.arange(d, dtype=torch.float64) + 100.0
+    uF[:I + 1] = keep
+    chunk, lo, cnt = slice_block(I, N, rank, world)
+    for s in range(lo, lo + cnt):                      # stand-in for the RK launch of this rank's block
+        uF[s + 1] = torch.arange(d, dtype=torch.float64) * 0.5 + s
+    gather_fine_rows(uF, I, chunk, rank, world)
+    want = torch.stack([torch.arange(d, dtype=torch.float64) * 0.5 + s for s in range(I, N)])
+    ok &= bool(torch.equal(uF[I + 1:N + 1], want)) and bool(torch.equal(uF[:I + 1], keep.expand(I + 1, d)))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+def test_time_slice_sharding_all_gather_gloo_world2(tmp_path):
+    """N>1 path on CPU: two ranks each fill their block of fine-solve rows, one all-gather, all rows everywhere"""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port]) for r in range(2)]
+    codes = [p.wait(timeout=180) for p in procs]
+    assert codes == [0, 0]
