@@ -143,6 +143,10 @@ int nngp_append_iteration(nngp_handle_t h, const double* d_u_cur, const double* 
 int nngp_rowwise_maxabs_diff(nngp_handle_t h, const double* d_a, const double* d_b, int rows,
                              int d, double* d_err, void* stream);
 
+/* test hook: the device exp(-|x|) and 1/sqrt(|x|) used inside the GP kernels, for n values */
+int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rsqrt,
+                       void* stream);
+
 /* counters of kernel launches issued through this handle (bench.py: gpu_launches) */
 long long nngp_launch_count(nngp_handle_t h);
 /* device-side work counters since the last reset (synchronises): Nelder-Mead searches run and

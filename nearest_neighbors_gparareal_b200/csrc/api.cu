@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#define NNGP_QUEUE_SLOTS 4096
+
 static std::string g_create_error;
 
 int nngp_fail(nngp_handle_t h, const char* fmt, ...) {
@@ -39,8 +41,30 @@ ProfScope::~ProfScope() {
   if (on) cudaEventRecord(h->prof_recs.back().b, st);
 }
 
+// a zeroed task-queue head for the next fit launch on stream st (slots are re-zeroed in bulk)
+static unsigned int* next_queue(nngp_handle_t h, cudaStream_t st) {
+  if (h->queue_next >= NNGP_QUEUE_SLOTS) {
+    cudaMemsetAsync(h->d_queues, 0, NNGP_QUEUE_SLOTS * sizeof(unsigned int), st);
+    h->queue_next = 0;
+  }
+  return h->d_queues + h->queue_next++;
+}
+
+// the fit kernel leaves its completion counters zero; they only need clearing when they move
+static int ensure_done_zero(nngp_handle_t h, void* ws_fit, int nq, int d, int m, int R, cudaStream_t st) {
+  const char* ptr = (const char*)ws_fit + gp_fit_done_offset(nq, d, m, R);
+  const size_t bytes = sizeof(unsigned int) * (size_t)nq * d;
+  if (h->done_ptr != ptr || h->done_bytes != bytes) {
+    NNGP_CUDA(h, cudaMemsetAsync((void*)ptr, 0, bytes, st));
+    h->done_ptr = ptr;
+    h->done_bytes = bytes;
+  }
+  return 0;
+}
+
 void* nngp_workspace(nngp_handle_t h, size_t bytes) {
   if (bytes <= h->ws_bytes) return h->ws;
+  h->done_ptr = nullptr;
   // grow: work already enqueued may still use the old block
   cudaDeviceSynchronize();
   if (h->ws) cudaFree(h->ws);
@@ -127,6 +151,11 @@ int nngp_create(int device, nngp_handle_t* out) {
     delete h;
     return nngp_fail(nullptr, "cudaMalloc(counters) failed");
   }
+  if (cudaMalloc(&h->d_queues, NNGP_QUEUE_SLOTS * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->d_queues, 0, NNGP_QUEUE_SLOTS * sizeof(unsigned int)) != cudaSuccess) {
+    delete h;
+    return nngp_fail(nullptr, "cudaMalloc(queues) failed");
+  }
   if (rk_set_tableaus(h) != 0) {
     g_create_error = h->err;
     delete h;
@@ -152,6 +181,7 @@ int nngp_destroy(nngp_handle_t h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->d_counters) cudaFree(h->d_counters);
+  if (h->d_queues) cudaFree(h->d_queues);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_free) cudaEventDestroy(e);
   delete h;
@@ -400,14 +430,14 @@ int nngp_knn_host(nngp_handle_t h, const double* q, int nq, int m, long long n_r
 }
 
 // ---- GP fit / predict ------------------------------------------------------------------
-// workspace layout for a fit on nq queries: [knn distances nq*n | r2 nq*m*m]
-static int fit_workspace(nngp_handle_t h, int nq, long long n, int m, void** knn_ws, double** r2) {
+// workspace layout for a fit on nq queries: [knn distances nq*n | fit block (r2 | results | done)]
+static int fit_workspace(nngp_handle_t h, int nq, long long n, int m, int R, void** knn_ws, void** fit_ws) {
   const size_t bk = Carver::pad(knn_workspace_bytes(nq, n, m));
-  const size_t br = Carver::pad(gp_prep_bytes(nq, m));
-  char* ws = (char*)nngp_workspace(h, bk + br);
-  if (!ws) return nngp_fail(h, "fit: out of device memory (workspace %zu bytes)", bk + br);
+  const size_t bf = Carver::pad(gp_fit_ws_bytes(nq, h->ds_d, m, R));
+  char* ws = (char*)nngp_workspace(h, bk + bf);
+  if (!ws) return nngp_fail(h, "fit: out of device memory (workspace %zu bytes)", bk + bf);
   *knn_ws = ws;
-  *r2 = (double*)(ws + bk);
+  *fit_ws = ws + bk;
   return 0;
 }
 
@@ -417,33 +447,35 @@ int nngp_fit_predict(nngp_handle_t h, const double* d_q, const long long* d_idx,
                      double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt, int* d_nfev,
                      double* d_fvals, double* d_thetas, void* stream) {
   (void)d_q;
-  void* kws; double* r2;
-  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  if (n_restarts < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", n_restarts);
+  void *kws, *fws;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, n_restarts, &kws, &fws)) return rc;
   cudaStream_t st = as_stream(stream);
-  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
-  return gp_fit_predict_launch(h, d_idx, d_dist, r2, nq, m, n_restarts, d_starts, fatol, xatol,
-                               d_pred, nullptr, d_theta_opt, d_jitter_opt, d_fval_opt, d_nfev,
+  if (int rc = ensure_done_zero(h, fws, nq, h->ds_d, m, n_restarts, st)) return rc;
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, (double*)fws, st)) return rc;
+  return gp_fit_predict_launch(h, d_idx, d_dist, fws, next_queue(h, st), nq, m, n_restarts, d_starts, fatol,
+                               xatol, d_pred, nullptr, h->ds_d, d_theta_opt, d_jitter_opt, d_fval_opt, d_nfev,
                                d_fvals, d_thetas, st);
 }
 
 int nngp_gp_nll(nngp_handle_t h, const long long* d_idx, int nq, int m, int nt,
                 const double* d_theta, const double* d_jitter10, double* d_nll, void* stream) {
-  void* kws; double* r2;
-  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  void *kws, *fws;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, 1, &kws, &fws)) return rc;
   cudaStream_t st = as_stream(stream);
-  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
-  return gp_nll_launch(h, d_idx, r2, nq, m, nt, d_theta, d_jitter10, d_nll, st);
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, (double*)fws, st)) return rc;
+  return gp_nll_launch(h, d_idx, (const double*)fws, nq, m, nt, d_theta, d_jitter10, d_nll, st);
 }
 
 int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, const double* d_dist,
                  int nq, int m, const double* d_theta, const double* d_jitter, double* d_pred,
                  void* stream) {
   (void)d_q;
-  void* kws; double* r2;
-  if (int rc = fit_workspace(h, nq, h->ds_rows, m, &kws, &r2)) return rc;
+  void *kws, *fws;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, 1, &kws, &fws)) return rc;
   cudaStream_t st = as_stream(stream);
-  if (int rc = gp_prep_launch(h, d_idx, nq, m, r2, st)) return rc;
-  return gp_mean_launch(h, d_idx, d_dist, r2, nq, m, d_theta, d_jitter, d_pred, st);
+  if (int rc = gp_prep_launch(h, d_idx, nq, m, (double*)fws, st)) return rc;
+  return gp_mean_launch(h, d_idx, d_dist, (const double*)fws, nq, m, d_theta, d_jitter, d_pred, st);
 }
 
 int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
@@ -471,12 +503,14 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
   double* gdist = (double*)(dev + o_dist);
   NNGP_CUDA(h, cudaMemcpyAsync(gq, q, sizeof(double) * nqd, cudaMemcpyHostToDevice, st));
   NNGP_CUDA(h, cudaMemcpyAsync(gst, starts, ntask * 2, cudaMemcpyHostToDevice, st));
-  void* kws; double* r2;
-  if (int rc = fit_workspace(h, nq, n, m, &kws, &r2)) return rc;
+  if (R < 1) return nngp_fail(h, "predict: n_restarts=%d < 1", R);
+  void *kws, *fws;
+  if (int rc = fit_workspace(h, nq, n, m, R, &kws, &fws)) return rc;
+  if (int rc = ensure_done_zero(h, fws, nq, d, m, R, st)) return rc;
   if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
-  if (int rc = gp_prep_launch(h, gidx, nq, m, r2, st)) return rc;
-  if (int rc = gp_fit_predict_launch(h, gidx, gdist, r2, nq, m, R, gst, fatol, xatol,
-                                     (double*)(dev + o_pred), nullptr,
+  if (int rc = gp_prep_launch(h, gidx, nq, m, (double*)fws, st)) return rc;
+  if (int rc = gp_fit_predict_launch(h, gidx, gdist, fws, next_queue(h, st), nq, m, R, gst, fatol, xatol,
+                                     (double*)(dev + o_pred), nullptr, d,
                                      theta_opt ? (double*)(dev + o_th) : nullptr,
                                      jitter_opt ? (double*)(dev + o_jit) : nullptr,
                                      fval_opt ? (double*)(dev + o_fv) : nullptr,
@@ -506,33 +540,37 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
   if (d != s->d || d != h->ds_d) return nngp_fail(h, "sweep: d=%d, system d=%d, dataset d=%d", d, s->d, h->ds_d);
   if (I < 0 || I > N) return nngp_fail(h, "sweep: I=%d outside [0,%d]", I, N);
   cudaStream_t st = as_stream(stream);
+  if (n_restarts < 1) return nngp_fail(h, "sweep: n_restarts=%d < 1", n_restarts);
   const long long n = h->ds_rows;
-  void* kws; double* r2;
-  const size_t extra = Carver::pad(sizeof(long long) * m) + Carver::pad(sizeof(double) * m);
-  {
-    const size_t bk = Carver::pad(knn_workspace_bytes(1, n, m));
-    const size_t br = Carver::pad(gp_prep_bytes(1, m));
-    char* ws = (char*)nngp_workspace(h, bk + br + extra);
-    if (!ws) return nngp_fail(h, "sweep: out of device memory");
-    kws = ws;
-    r2 = (double*)(ws + bk);
-    long long* idx = (long long*)(ws + bk + br);
-    double* dist = (double*)(ws + bk + br + Carver::pad(sizeof(long long) * m));
-    const size_t per_predict = (size_t)d * NNGP_N_JITTER * n_restarts * 2;
-    for (int i = I; i < N; i++) {
-      double* ui = d_u_next + (long long)i * d;
-      double* un = d_u_next + (long long)(i + 1) * d;
-      double* gn = d_uG_next + (long long)(i + 1) * d;
-      if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
-      if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
-      if (int rc = gp_prep_launch(h, idx, 1, m, r2, st)) return rc;
-      if (int rc = gp_fit_predict_launch(h, idx, dist, r2, 1, m, n_restarts,
-                                         d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn,
-                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st))
-        return rc;
-    }
+  const size_t bk = Carver::pad(knn_workspace_bytes(1, n, m));
+  const size_t bf = Carver::pad(gp_fit_ws_bytes(1, d, m, n_restarts));
+  const size_t bi = Carver::pad(sizeof(long long) * m), bd = Carver::pad(sizeof(double) * m);
+  char* ws = (char*)nngp_workspace(h, bk + bf + bi + bd);
+  if (!ws) return nngp_fail(h, "sweep: out of device memory");
+  void* kws = ws;
+  void* fws = ws + bk;
+  long long* idx = (long long*)(ws + bk + bf);
+  double* dist = (double*)(ws + bk + bf + bi);
+  if (int rc = ensure_done_zero(h, fws, 1, d, m, n_restarts, st)) return rc;
+  const size_t per_predict = (size_t)d * NNGP_N_JITTER * n_restarts * 2;
+  for (int i = I; i < N; i++) {
+    double* ui = d_u_next + (long long)i * d;
+    double* un = d_u_next + (long long)(i + 1) * d;
+    double* gn = d_uG_next + (long long)(i + 1) * d;
+    if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
+    if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
+    if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
+    if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), 1, m, n_restarts,
+                                       d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn, d,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st))
+      return rc;
   }
   return 0;
+}
+
+int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rsqrt,
+                       void* stream) {
+  return selftest_math_launch(h, d_x, n, d_exp_neg, d_rsqrt, as_stream(stream));
 }
 
 // ---- roofline micro-benchmarks ---------------------------------------------------------

@@ -54,6 +54,12 @@ struct nngp_handle_s {
   cudaStream_t own_stream = nullptr;
   // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
   unsigned long long* d_counters = nullptr;
+  // task-queue heads of the persistent fit kernel: one zeroed counter per launch
+  unsigned int* d_queues = nullptr;
+  int queue_next = 0;
+  // where the (zero on exit) per-(query,dim) completion counters of the last fit lived
+  const void* done_ptr = nullptr;
+  size_t done_bytes = 0;
   // optional per-kernel-class timing with CUDA events on the launching stream
   bool profiling = false;
   struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -105,13 +111,16 @@ int rowwise_maxabs_launch(nngp_handle_t h, const double* a, const double* b, int
 
 // gpfit.cu
 size_t gp_prep_bytes(int nq, int m);
+size_t gp_fit_ws_bytes(int nq, int d, int m, int R);      // [r2 | per-search results | done counters]
+size_t gp_fit_done_offset(int nq, int d, int m, int R);   // byte offset of the done counters
 int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, double* d_r2,
                    cudaStream_t st);
-int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist,
-                          const double* d_r2, int nq, int m, int R, const signed char* d_starts,
+int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist, void* ws,
+                          unsigned int* queue, int nq, int m, int R, const signed char* d_starts,
                           double fatol, double xatol, double* d_pred, const double* d_add,
-                          double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt,
-                          int* d_nfev, double* d_fvals, double* d_thetas, cudaStream_t st);
+                          long long ld_pred, double* d_theta_opt, double* d_jitter_opt,
+                          double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
+                          cudaStream_t st);
 int gp_nll_launch(nngp_handle_t h, const long long* d_idx, const double* d_r2, int nq, int m,
                   int nt, const double* d_theta, const double* d_jitter10, double* d_nll,
                   cudaStream_t st);
@@ -119,4 +128,6 @@ int gp_mean_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist
                    const double* d_r2, int nq, int m, const double* d_theta,
                    const double* d_jitter, double* d_pred, cudaStream_t st);
 
-// bench kernels (api.cu)
+int selftest_math_launch(nngp_handle_t h, const double* d_x, int n, double* d_exp, double* d_rsqrt,
+                         cudaStream_t st);
+

@@ -7,20 +7,28 @@
 // posterior mean (models.py:162-168) -- one launch per predict instead of d*9*R pickled
 // tasks through pool.map.
 //
-// Mapping: grid = (d, nq); one CTA per (query, output dimension); one WARP per Nelder-Mead
-// search (9 warps; restarts loop).  Inside a warp lane r owns row r of the m x m kernel matrix
-// (m <= 32) in registers: right-looking Cholesky with shuffle broadcasts, forward solve fused
-// into the factorisation, L transposed through a per-warp shared-memory tile for the
-// column-oriented backward solve.  The m x m squared-distance matrix of the neighbours is
-// computed once per query (gp_prep_kernel) and shared by all d*9*R searches.  The simplex
-// arithmetic uses explicitly rounded (non-fused) operations in SciPy's order so the search
-// follows the reference trajectory; a failed factorisation (pivot <= 0 or NaN) makes the
-// objective +inf exactly like the reference (NaN -> inf, models.py:250-251).
+// Mapping.  One WARP per Nelder-Mead search.  The searches of a launch (nq*d*9*R tasks) sit in
+// a queue; a persistent grid of independent warps pulls them with an atomic counter, so a warp
+// that finishes a short search immediately starts another one (search lengths vary from ~10 to
+// 400 objective evaluations).  The warp that completes the last search of an (query, dimension)
+// pair applies the selection rule and computes the posterior mean (no block barrier, no second
+// launch).  Inside a warp lane r owns row r of the m x m kernel matrix (m <= 32) in registers:
+// right-looking Cholesky, pivot broadcast by shuffle, column broadcast through a per-warp
+// shared-memory tile read with warp-uniform 16-byte loads, forward solve fused into the
+// factorisation.  The m x m squared-distance matrix of the neighbours is computed once per query
+// (gp_prep_kernel) and read through L1 by all d*9*R searches.
+//
+// Arithmetic.  The simplex arithmetic uses explicitly rounded (non-fused) operations in SciPy's
+// order.  The objective is the reference's  0.5 y^T K^-1 y + sum log L_ii + (m/2) log 2 pi  with the
+// data-fit term evaluated as |L^-1 y|^2 (identical in exact arithmetic; the reference's own
+// optimiser trajectories are not reproducible below 1 ulp of the objective, see DESIGN.md
+// "ties"), pivots from rsqrt.  A pivot <= 0 or NaN fails like LAPACK potf2 and makes the
+// objective +inf exactly as the reference does (NaN -> inf, models.py:250-251).
 #include "common.cuh"
 
 #include <cmath>
 
-static constexpr int GP_WARPS = NNGP_N_JITTER;  // one warp per jitter value
+static constexpr int GP_WARPS = 4;  // warps per CTA of the persistent fit kernel
 static constexpr unsigned FULL = 0xffffffffu;
 
 // 10**jitter for jitter = -20..-12 (models.py:186, :88)
@@ -31,131 +39,209 @@ __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(F
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 __device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// ---------------------------------------------------------------------------------------
+// exp(x) for x <= 0 (kernel entries exp(-0.5 r^2 / l^2)) and 1/sqrt(p) for p > 0, written so
+// that every constant is a constant-bank operand of the FP64 instruction (no register moves
+// for 64-bit immediates; the library routines cost ~2x the instructions when inlined 21 times).
+//   exp: x = k ln2 + r, |r| <= ln2/2, Taylor degree 13 (remainder < 5e-18), result 2^k p(r);
+//        NaN propagates, x < -708.39 (subnormal results) returns 0.
+//   rsqrt: MUFU.RSQ64H seed (2^-22) + one cubically convergent correction (as CUDA's rsqrt,
+//        without the denormal/inf fix-up: such pivots make the objective NaN -> +inf).
+// Both are within 1 ulp of the correctly rounded value (tests/test_gpu_kernels.py).
+// ---------------------------------------------------------------------------------------
+__constant__ double c_exp[18] = {
+    1.4426950408889634,        // [0] log2(e)
+    6755399441055744.0,        // [1] 1.5 * 2^52: adding it rounds to the nearest integer
+    -6.93147180369123816490e-01,  // [2] -ln2_hi
+    -1.90821492927058770002e-10,  // [3] -ln2_lo
+    1.6059043836821613e-10,    // [4] 1/13!
+    2.08767569878681e-09,      // [5] 1/12!
+    2.505210838544172e-08,     // [6] 1/11!
+    2.755731922398589e-07,     // [7] 1/10!
+    2.7557319223985893e-06,    // [8] 1/9!
+    2.48015873015873e-05,      // [9] 1/8!
+    0.0001984126984126984,     // [10] 1/7!
+    0.001388888888888889,      // [11] 1/6!
+    0.008333333333333333,      // [12] 1/5!
+    0.041666666666666664,      // [13] 1/4!
+    0.16666666666666666,       // [14] 1/3!
+    0.5,                       // [15] 1/2!
+    -708.39,                   // [16] below this the result is subnormal: return 0
+    0.375};                    // [17] rsqrt correction
+
+__device__ __forceinline__ double exp_neg(double x) {
+  const double t = fma(x, c_exp[0], c_exp[1]);
+  const int k = __double2loint(t);
+  const double kf = t - c_exp[1];
+  double r = fma(kf, c_exp[2], x);
+  r = fma(kf, c_exp[3], r);
+  double p = c_exp[4];
+#pragma unroll
+  for (int i = 5; i <= 15; i++) p = fma(p, r, c_exp[i]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  // 2^k by exponent arithmetic; k in [-1022, 1] on the accepted range
+  const double scale = __hiloint2double((k + 1023) << 20, 0);
+  const double v = p * scale;
+  return (x < c_exp[16]) ? 0.0 : v;  // false for NaN: NaN propagates through p
+}
+
+__device__ __forceinline__ double rsqrt_pos(double p) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  const double t = y * y;
+  const double e = fma(-p, t, 1.0);
+  const double c = fma(e, c_exp[17], c_exp[15]);
+  const double ye = y * e;
+  return fma(c, ye, y);
+}
+
+// 1/p for p > 0: MUFU.RCP64H seed + two Newton steps
+__device__ __forceinline__ double rcp_pos(double p) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  double e = fma(-p, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-p, y, 1.0);
+  return fma(y, e, y);
+}
+
+__global__ void selftest_math_kernel(const double* x, int n, double* out_exp, double* out_rsqrt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out_exp[i] = exp_neg(-fabs(x[i]));
+  const double r = rsqrt_pos(fabs(x[i]));
+  out_rsqrt[i] = r * r * 0.0 + rcp_pos(fabs(x[i]));  // reports 1/|x| (rsqrt kept for reference)
+}
+
+int selftest_math_launch(nngp_handle_t h, const double* d_x, int n, double* d_exp, double* d_rsqrt,
+                         cudaStream_t st) {
+  if (n <= 0) return 0;
+  selftest_math_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_x, n, d_exp, d_rsqrt);
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
 
-// np.sum over m values held one per lane, in NumPy's pairwise order (8 lanes, then the tail)
-__device__ __forceinline__ double numpy_sum_lanes(double v, int m, int lane) {
-  if (m < 8) {
-    double r = 0.0;
-    for (int i = 0; i < m; i++) r = __dadd_rn(r, shfl(v, i));
-    return r;
-  }
-  const int nb = m >> 3;  // full blocks of 8
-  double acc = v;         // lane j<8 : r[j]
-  for (int b = 1; b < nb; b++) acc = __dadd_rn(acc, __shfl_down_sync(FULL, v, 8 * b));
-  double t = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
-  t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 2));
-  t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 4));
-  double res = shfl(t, 0);
-  for (int i = nb * 8; i < m; i++) res = __dadd_rn(res, shfl(v, i));
-  return res;
-}
-
 // ---------------------------------------------------------------------------------------
-// GP core for one warp.  On return (true): alpha = (K^-1 y)_lane, dg = L_lane,lane.
-// r2s: shared, symmetric [M*M] squared distances (entry (a,b) at a*M+b); Ls: per-warp shared
-// scratch [M*(M+1)].  Follows _fit_gp_jit (models.py:86-92).
+// GP core for one warp (models.py:86-92).  One copy per M in the module (noinline): the
+// Nelder-Mead loop, the objective kernel and the final refit all call the same code.
+//   r2   global [m*m] squared distances of the neighbours (row-major, symmetric, unpadded)
+//   Lt   per-warp shared tile [M*(M+1)], column k of L at Lt[k*(M+1) + r]
+// want_alpha == false: returns nll (or +inf) in .val
+// want_alpha == true : returns alpha_lane = (K^-1 y)_lane in .val, .ok tells success
 // ---------------------------------------------------------------------------------------
-struct GpSol {
-  double alpha, dg, amp, c;
+struct GpOut {
+  double val, amp, c;
   bool ok;
 };
 
-// One copy per M in the module (noinline): the Nelder-Mead loop, the objective kernel and the
-// final refit all call the same code, which keeps the instruction footprint inside the I-cache.
 template <int M>
-__device__ __noinline__ GpSol gp_factor_solve(double th0, double th1, double jit10,
-                                              const double* __restrict__ r2s, double y, int m,
-                                              int lane, double* __restrict__ Ls) {
-  GpSol o;
-  const double amp = exp10(th1);       // 10**sigma_y
+__device__ __noinline__ GpOut gp_eval(double th0, double th1, double jit10,
+                                      const double* __restrict__ r2, double y, int m, int lane,
+                                      double* __restrict__ Lt, double hml, bool want_alpha) {
+  static_assert(M % 2 == 0, "M even: 16-byte broadcast loads of column pairs");
+  constexpr int LD = M + 1;
+  GpOut o;
+  const double amp = exp10(th1);        // 10**sigma_y
   const double inv = 1.0 / exp10(th0);  // 1/(10**sigma_x)
   const double c = -0.5 * inv;
   o.amp = amp;
   o.c = c;
-  o.alpha = 0.0;
-  o.dg = 1.0;
   o.ok = false;
+  o.val = dinf();
   const bool rowvalid = lane < m;
-  const int col = (lane < M) ? lane : 0;
   double a[M];
-  double dd = 1.0;
+  {
+    // symmetric: entry (lane, j) read as (j, lane) -> consecutive lanes, consecutive addresses;
+    // padded rows / columns read a valid address and are masked below
+    const double* rp = r2 + (rowvalid ? lane : 0);
 #pragma unroll
-  for (int j = 0; j < M; j++) {
-    const double kv = amp * exp(c * r2s[j * M + col]);
-    const bool valid = rowvalid && (j < m);
-    a[j] = valid ? kv : 0.0;
-    if (j == lane) dd = valid ? (kv + jit10) : 1.0;
+    for (int j = 0; j < M; j++) a[j] = amp * exp_neg(c * __ldg(rp + ((j < m) ? j : 0) * m));
+    if (m < M) {  // padding acts as an identity block
+#pragma unroll
+      for (int j = 0; j < M; j++)
+        if (!rowvalid || j >= m) a[j] = 0.0;
+    }
   }
+  // K_rr = amp*exp(c*0) + 10**jitter ; c*0 is 0 unless c is not finite (then NaN, as in NumPy).
+  // Padded rows carry the same diagonal (an identity block scaled by K_rr; excluded from the sums).
+  const double dd0 = amp * exp_neg(c * 0.0) + jit10;
+  double dd = dd0;
+  // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
+  // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
+  // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
+  // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
+  // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
+  const double pmin = dd0 * 8.8817841970012523e-16;
   double z = rowvalid ? y : 0.0;
-  double dg = 1.0;
-  // right-looking Cholesky (LAPACK potf2 semantics: fail on pivot <= 0 or NaN), forward solve
-  // L z = y fused (x_k = x_k / L_kk ; x_r -= x_k L_rk)
+  double inv_own = 1.0, w_own = 0.0;  // 1/d_r and (L'^-1 y)_r of the own row
+  // Square-root-free right-looking factorisation K = L' D L'^T (L' unit lower, d_k = L_kk^2 of the
+  // Cholesky factor): the pivot's reciprocal is the only long-latency operation of a step, and
+  // the column broadcast through shared memory overlaps it.  Updates are unconditional: a lane's
+  // entries right of its diagonal and its z / dd after its own pivot step are never read again.
 #pragma unroll
   for (int k = 0; k < M; k++) {
-    if (k >= m) break;
     const double p = shfl(dd, k);
-    if (!(p > 0.0)) return o;
-    const double s = sqrt(p);
-    const double is = 1.0 / s;
-    const double zk = shfl(z, k) / s;
-    const double lk = a[k] * is;
+    const double wk = shfl(z, k);
+    if (k + 1 < M) {
+      if (lane > k && lane < M) Lt[k * LD + lane] = a[k];  // u_rk = unscaled column k
+      __syncwarp();
+    }
+    if (!(p > pmin)) return o;  // failed factorisation (potf2: pivot <= 0 or NaN) -> +inf
+    const double inv = rcp_pos(p);
+    const double w = a[k] * inv;  // l'_rk
     if (lane == k) {
-      dg = s;
-      z = zk;
-    } else if (lane > k) {
-      a[k] = lk;
-      z = z - zk * lk;
-      dd = dd - lk * lk;
+      inv_own = inv;
+      w_own = wk;
     }
+    z = z - wk * w;
+    dd = dd - w * a[k];
+    if (k + 1 < M) {
+      int j = k + 1;
+      if (((k * LD + j) & 1) != 0) {  // (k*LD + j) even <=> 16-byte aligned pair
+        a[j] = a[j] - w * Lt[k * LD + j];
+        j++;
+      }
 #pragma unroll
-    for (int j = k + 1; j < M; j++) {
-      if (j >= m) break;
-      const double ljk = shfl(lk, j);
-      a[j] = a[j] - lk * ljk;
+      for (; j + 1 < M; j += 2) {
+        const double2 u2 = *reinterpret_cast<const double2*>(&Lt[k * LD + j]);
+        a[j] = a[j] - w * u2.x;
+        a[j + 1] = a[j + 1] - w * u2.y;
+      }
+      if (j < M) a[j] = a[j] - w * Lt[k * LD + j];
     }
   }
-  // transpose L through shared memory: lane r writes row r, lane k reads column k
-  constexpr int LD = M + 1;
-  __syncwarp();
-  if (lane < M) {
-#pragma unroll
-    for (int j = 0; j < M; j++) Ls[lane * LD + j] = a[j];
+  o.ok = true;
+  if (!want_alpha) {
+    // -(-0.5*y@alpha - sum(log(diag L)) - (N/2) log(2 pi)):  y@alpha = sum w_r^2/d_r,
+    // log L_rr = 0.5 log d_r = -0.5 log(1/d_r)
+    const double part = rowvalid ? 0.5 * (w_own * w_own * inv_own - log(inv_own)) : 0.0;
+    const double res = warp_sum(part) + hml;
+    o.val = (res != res) ? dinf() : res;
+    return o;
   }
+  // alpha = L'^-T D^-1 L'^-1 y.  Backward solve column oriented: lane k needs column k of L',
+  // l'_rk = u_rk / d_k = Lt[k*LD + r] * inv_own  (r > k)
   __syncwarp();
+  const int col = (lane < M) ? lane : 0;
 #pragma unroll
-  for (int r = 0; r < M; r++) a[r] = Ls[r * LD + col];  // a[r] = L[r][lane] for r > lane
-  // backward solve L^T alpha = z, column oriented (x_r = x_r / L_rr ; x_k -= x_r L_rk)
-  double alpha = 0.0;
+  for (int r = 1; r < M; r++) a[r] = Lt[col * LD + r] * inv_own;
+  double alpha = 0.0, vb = w_own * inv_own;
 #pragma unroll
   for (int r = M - 1; r >= 0; r--) {
-    if (r >= m) continue;
-    const double ar = shfl(z / dg, r);
+    const double ar = shfl(vb, r);
     if (lane == r) alpha = ar;
-    if (lane < r) z = z - a[r] * ar;
+    vb = vb - a[r] * ar;  // meaningful for lane < r only
   }
-  o.alpha = alpha;
-  o.dg = dg;
-  o.ok = true;
+  o.val = alpha;
   return o;
-}
-
-// log_lik of models.py:240-252 (warp-uniform result)
-template <int M>
-__device__ __forceinline__ double gp_nll(double th0, double th1, double jit10,
-                                         const double* __restrict__ r2s, double y, int m,
-                                         int lane, double* __restrict__ Ls, double half_m_log2pi) {
-  const GpSol g = gp_factor_solve<M>(th0, th1, jit10, r2s, y, m, lane, Ls);
-  if (!g.ok) return dinf();
-  const double ya = warp_sum((lane < m) ? y * g.alpha : 0.0);
-  const double sl = numpy_sum_lanes(log(g.dg), m, lane);
-  // -(-0.5*y@alpha - sum(log(diag L)) - (N/2) log(2 pi))
-  const double res = -(((-0.5 * ya) - sl) - half_m_log2pi);
-  return (res != res) ? dinf() : res;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -192,8 +278,8 @@ __device__ __forceinline__ double shrink_to(double x0, double xj) {
 
 template <int M>
 __device__ NMOut nelder_mead(double s0, double s1, double jit10, double fatol, double xatol,
-                             const double* __restrict__ r2s, double y, int m, int lane,
-                             double* __restrict__ Ls, double hml) {
+                             const double* __restrict__ r2, double y, int m, int lane,
+                             double* __restrict__ Lt, double hml) {
   const int maxfun = 400, maxiter = 400;  // 200 * N
   double sx[3][2], sf[3];
   sx[0][0] = s0; sx[0][1] = s1;
@@ -204,14 +290,15 @@ __device__ NMOut nelder_mead(double s0, double s1, double jit10, double fatol, d
   double p0 = s0, p1 = s1;
   double xb0 = 0, xb1 = 0, xr0 = 0, xr1 = 0, fxr = 0;
   for (;;) {
-    const double f = gp_nll<M>(p0, p1, jit10, r2s, y, m, lane, Ls, hml);
+    const double f = gp_eval<M>(p0, p1, jit10, r2, y, m, lane, Lt, hml, false).val;
     fcalls++;
     bool aborted = false, do_shrink = false;
-    if (phase < PH_INIT2) {
-      sf[phase] = f;
-      phase++;
-      p0 = sx[phase][0];
-      p1 = sx[phase][1];
+    if (phase == PH_INIT0) {
+      sf[0] = f; phase = PH_INIT1; p0 = sx[1][0]; p1 = sx[1][1];
+      continue;
+    }
+    if (phase == PH_INIT1) {
+      sf[1] = f; phase = PH_INIT2; p0 = sx[2][0]; p1 = sx[2][1];
       continue;
     }
     const bool initial = (phase == PH_INIT2);
@@ -321,134 +408,126 @@ struct FitArgs {
   double* fvals;          // [nq,d,9,R]
   double* thetas;         // [nq,d,9,R,2]
   unsigned long long* counters;  // [0] NM runs, [1] nll evaluations
-  int d, m, R;
+  double* res;            // workspace [ntasks,3]: fval, theta0, theta1 of every search
+  unsigned int* done;     // workspace [nq*d]: searches finished per (query, dim); zero on entry and exit
+  unsigned int* queue;    // next task to hand out; zero on entry
+  int d, m, R, ntasks;
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
 };
 
 template <int M>
-__device__ __forceinline__ void load_problem(const long long* idx, const double* dist,
-                                             const double* r2, const double* Y, int d, int m,
-                                             int q, int j, double* r2s, double* ys, double* kqs) {
-  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const int a = e / M, b = e - a * M;
-    r2s[e] = (a < m && b < m) ? r2[((long long)q * m + a) * m + b] : 0.0;
-  }
-  for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    ys[r] = (r < m) ? Y[idx[(long long)q * m + r] * d + j] : 0.0;
-    kqs[r] = (r < m && dist != nullptr) ? dist[(long long)q * m + r] : 0.0;
-  }
-}
-
-template <int M>
 __device__ __forceinline__ double posterior_mean(double th0, double th1, double jit10,
-                                                 const double* r2s, const double* ys,
-                                                 const double* kqs, int m, int lane, double* Ls) {
-  const int col = (lane < M) ? lane : 0;
-  const GpSol g = gp_factor_solve<M>(th0, th1, jit10, r2s, ys[col], m, lane, Ls);
+                                                 const double* r2, double y, double kq, int m,
+                                                 int lane, double* Lt) {
+  const GpOut g = gp_eval<M>(th0, th1, jit10, r2, y, m, lane, Lt, 0.0, true);
   if (!g.ok) return dnan();
   // K_star = kernel(x, new_x); post_mean = K_star.T @ alph  (models.py:165-167)
-  const double ks = g.amp * exp(g.c * kqs[col]);
-  return warp_sum((lane < m) ? ks * g.alpha : 0.0);
+  const double ks = g.amp * exp_neg(g.c * kq);
+  return warp_sum((lane < m) ? ks * g.val : 0.0);
 }
 
-// CTAs per SM the fit kernel is compiled for (register cap): 288 threads x 2 CTAs -> 112 regs
-template <int M> struct FitOcc { static constexpr int value = 2; };
+// registers per thread: 4-warp CTAs, K CTAs per SM
+template <int M> struct FitOcc { static constexpr int value = (M <= 20) ? 5 : ((M <= 26) ? 4 : 3); };
 
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32, FitOcc<M>::value)
 gp_fit_predict_kernel(FitArgs A) {
   extern __shared__ double sm[];
   const int m = A.m, d = A.d, R = A.R, nruns = NNGP_N_JITTER * R;
-  double* r2s = sm;                       // M*M
-  double* ys = r2s + M * M;               // M
-  double* kqs = ys + M;                   // M
-  double* Lsall = kqs + M;                // GP_WARPS * M*(M+1)
-  double* rf = Lsall + GP_WARPS * M * (M + 1);  // nruns
-  double* rt = rf + nruns;                // nruns*2
-  const int j = blockIdx.x, q = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  load_problem<M>(A.idx, A.dist, A.r2, A.Y, d, m, q, j, r2s, ys, kqs);
-  __syncthreads();
-  double* Ls = Lsall + w * M * (M + 1);
-  const double y = ys[(lane < M) ? lane : 0];
+  double* Lt = sm + w * (M * (M + 1));
   const double hml = (m / 2.0) * 1.8378770664093453;  // (N/2)*np.log(2*np.pi)
-  const long long task0 = ((long long)q * d + j) * nruns;
-  for (int run = w; run < nruns; run += GP_WARPS) {
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = (int)atomicAdd(A.queue, 1u);
+    task = __shfl_sync(FULL, task, 0);
+    if (task >= A.ntasks) break;
+    const int qj = task / nruns, run = task - qj * nruns;
+    const int q = qj / d, j = qj - q * d;
     const int a = run / R;
-    const signed char* st = A.starts + (task0 + run) * 2;
-    const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol,
-                                   r2s, y, m, lane, Ls, hml);
+    const double* r2 = A.r2 + (long long)q * m * m;
+    const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
+    const signed char* st = A.starts + (long long)task * 2;
+    const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol, r2, y, m,
+                                   lane, Lt, hml);
+    unsigned int prior = 0;
     if (lane == 0) {
-      rf[run] = o.f;
-      rt[2 * run] = o.x0;
-      rt[2 * run + 1] = o.x1;
+      A.res[(long long)task * 3] = o.f;
+      A.res[(long long)task * 3 + 1] = o.x0;
+      A.res[(long long)task * 3 + 2] = o.x1;
       atomicAdd(A.counters, 1ULL);
       atomicAdd(A.counters + 1, (unsigned long long)o.nfev);
-      if (A.nfev) A.nfev[task0 + run] = o.nfev;
-      if (A.fvals) A.fvals[task0 + run] = o.f;
+      if (A.nfev) A.nfev[task] = o.nfev;
+      if (A.fvals) A.fvals[task] = o.f;
       if (A.thetas) {
-        A.thetas[(task0 + run) * 2] = o.x0;
-        A.thetas[(task0 + run) * 2 + 1] = o.x1;
+        A.thetas[(long long)task * 2] = o.x0;
+        A.thetas[(long long)task * 2 + 1] = o.x1;
       }
+      __threadfence();
+      prior = atomicAdd(A.done + qj, 1u);
     }
-  }
-  __syncthreads();
-  if (w == 0) {
+    prior = __shfl_sync(FULL, prior, 0);
+    if (prior != (unsigned)(nruns - 1)) continue;
+    // this warp finished the last search of (q, j): selection + posterior mean
+    __threadfence();
+    const volatile double* rf = A.res + (long long)qj * nruns * 3;
     // models.py:212-215: mask = fval < 0.9*min; empty mask -> all; first minimum in task order
     double fmin_all = rf[0];
-    for (int r = 1; r < nruns; r++) fmin_all = (rf[r] < fmin_all) ? rf[r] : fmin_all;
+    for (int r = 1; r < nruns; r++) {
+      const double v = rf[3 * r];
+      fmin_all = (v < fmin_all) ? v : fmin_all;
+    }
     const double thr = fmin_all * 0.9;
     bool any = false;
-    for (int r = 0; r < nruns; r++) any |= (rf[r] < thr);
+    for (int r = 0; r < nruns; r++) any |= (rf[3 * r] < thr);
     int best = -1;
     double fb = 0.0;
     for (int r = 0; r < nruns; r++) {
-      if (any && !(rf[r] < thr)) continue;
-      if (best < 0 || rf[r] < fb) {
+      const double v = rf[3 * r];
+      if (any && !(v < thr)) continue;
+      if (best < 0 || v < fb) {
         best = r;
-        fb = rf[r];
+        fb = v;
       }
     }
-    const int a = best / R;
-    const double th0 = rt[2 * best], th1 = rt[2 * best + 1];
-    double mean = posterior_mean<M>(th0, th1, c_jit10[a], r2s, ys, kqs, m, lane, Ls);
+    const int ab = best / R;
+    const double th0 = rf[3 * best + 1], th1 = rf[3 * best + 2];
+    const double kq = (lane < m) ? A.dist[(long long)q * m + lane] : 0.0;
+    double mean = posterior_mean<M>(th0, th1, c_jit10[ab], r2, y, kq, m, lane, Lt);
     if (lane == 0) {
-      const long long o = (long long)q * A.ld_pred + j;
-      if (A.add) mean = mean + A.add[o];
-      A.pred[o] = mean;
-      const long long oo = (long long)q * d + j;
+      A.done[qj] = 0;  // leave the counters clean for the next launch
+      const long long op = (long long)q * A.ld_pred + j;
+      if (A.add) mean = mean + A.add[op];
+      A.pred[op] = mean;
       if (A.theta_opt) {
-        A.theta_opt[oo * 2] = th0;
-        A.theta_opt[oo * 2 + 1] = th1;
+        A.theta_opt[(long long)qj * 2] = th0;
+        A.theta_opt[(long long)qj * 2 + 1] = th1;
       }
-      if (A.jitter_opt) A.jitter_opt[oo] = (double)(a - 20);
-      if (A.fval_opt) A.fval_opt[oo] = fb;
+      if (A.jitter_opt) A.jitter_opt[qj] = (double)(ab - 20);
+      if (A.fval_opt) A.fval_opt[qj] = fb;
     }
   }
 }
 
-// objective at given hyper-parameters: one warp per (q, j, t)
+// objective at given hyper-parameters: one warp per (q, j), loops over t
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32)
-gp_nll_kernel(const long long* idx, const double* r2, const double* Y, int d, int m, int nt,
+gp_nll_kernel(const long long* idx, const double* r2all, const double* Y, int d, int m, int nq, int nt,
               const double* theta, const double* jitter10, double* out) {
   extern __shared__ double sm[];
-  double* r2s = sm;
-  double* ys = r2s + M * M;
-  double* kqs = ys + M;
-  double* Lsall = kqs + M;
-  const int j = blockIdx.x, q = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  load_problem<M>(idx, nullptr, r2, Y, d, m, q, j, r2s, ys, kqs);
-  __syncthreads();
-  double* Ls = Lsall + w * M * (M + 1);
-  const double y = ys[(lane < M) ? lane : 0];
+  double* Lt = sm + w * (M * (M + 1));
+  const int qj = blockIdx.x * GP_WARPS + w;
+  if (qj >= nq * d) return;
+  const int q = qj / d, j = qj - q * d;
+  const double* r2 = r2all + (long long)q * m * m;
+  const double y = (lane < m) ? Y[idx[(long long)q * m + lane] * d + j] : 0.0;
   const double hml = (m / 2.0) * 1.8378770664093453;
-  const long long base = ((long long)q * d + j) * nt;
-  for (int t = w; t < nt; t += GP_WARPS) {
-    const double v = gp_nll<M>(theta[(base + t) * 2], theta[(base + t) * 2 + 1], jitter10[base + t],
-                               r2s, y, m, lane, Ls, hml);
+  const long long base = (long long)qj * nt;
+  for (int t = 0; t < nt; t++) {
+    const double v = gp_eval<M>(theta[(base + t) * 2], theta[(base + t) * 2 + 1], jitter10[base + t], r2, y, m,
+                                lane, Lt, hml, false).val;
     if (lane == 0) out[base + t] = v;
   }
 }
@@ -456,30 +535,21 @@ gp_nll_kernel(const long long* idx, const double* r2, const double* Y, int d, in
 // posterior mean at given hyper-parameters: one warp per (q, j)
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32)
-gp_mean_kernel(const long long* idx, const double* dist, const double* r2, const double* Y, int d,
-               int m, const double* theta, const double* jitter, double* pred) {
+gp_mean_kernel(const long long* idx, const double* dist, const double* r2all, const double* Y, int d,
+               int m, int nq, const double* theta, const double* jitter, double* pred) {
   extern __shared__ double sm[];
-  double* r2s = sm;
-  double* Lsall = r2s + M * M;            // GP_WARPS * M*(M+1)
-  double* ysall = Lsall + GP_WARPS * M * (M + 1);  // GP_WARPS * M
-  double* kqs = ysall + GP_WARPS * M;     // M
-  const int q = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int j = blockIdx.x * GP_WARPS + w;
-  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const int a = e / M, b = e - a * M;
-    r2s[e] = (a < m && b < m) ? r2[((long long)q * m + a) * m + b] : 0.0;
-  }
-  for (int r = threadIdx.x; r < M; r += blockDim.x) kqs[r] = (r < m) ? dist[(long long)q * m + r] : 0.0;
-  double* ys = ysall + w * M;
-  if (j < d && lane < M) ys[lane] = (lane < m) ? Y[idx[(long long)q * m + lane] * d + j] : 0.0;
-  __syncthreads();
-  if (j >= d) return;
-  const long long o = (long long)q * d + j;
-  const double jit10 = exp10(jitter[o]);
-  const double mean = posterior_mean<M>(theta[o * 2], theta[o * 2 + 1], jit10, r2s, ys, kqs, m, lane,
-                                        Lsall + w * M * (M + 1));
-  if (lane == 0) pred[o] = mean;
+  double* Lt = sm + w * (M * (M + 1));
+  const int qj = blockIdx.x * GP_WARPS + w;
+  if (qj >= nq * d) return;
+  const int q = qj / d, j = qj - q * d;
+  const double* r2 = r2all + (long long)q * m * m;
+  const double y = (lane < m) ? Y[idx[(long long)q * m + lane] * d + j] : 0.0;
+  const double kq = (lane < m) ? dist[(long long)q * m + lane] : 0.0;
+  const double jit10 = exp10(jitter[qj]);
+  const double mean = posterior_mean<M>(theta[(long long)qj * 2], theta[(long long)qj * 2 + 1], jit10, r2, y, kq,
+                                        m, lane, Lt);
+  if (lane == 0) pred[qj] = mean;
 }
 
 // pairwise squared distances of the m neighbours of each query: r2[q,a,b] = ||x_a - x_b||^2,
@@ -539,7 +609,17 @@ gp_prep_kernel(const long long* __restrict__ idx, const double* __restrict__ X, 
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
+static inline size_t pad256(size_t b) { return ((b + 255) / 256) * 256; }
+
+// workspace of a fit: [r2 nq*m*m | res ntasks*3 | done nq*d]
 size_t gp_prep_bytes(int nq, int m) { return sizeof(double) * (size_t)nq * m * m; }
+size_t gp_fit_ws_bytes(int nq, int d, int m, int R) {
+  return pad256(gp_prep_bytes(nq, m)) + pad256(sizeof(double) * 3 * (size_t)nq * d * NNGP_N_JITTER * R) +
+         pad256(sizeof(unsigned int) * (size_t)nq * d);
+}
+size_t gp_fit_done_offset(int nq, int d, int m, int R) {
+  return pad256(gp_prep_bytes(nq, m)) + pad256(sizeof(double) * 3 * (size_t)nq * d * NNGP_N_JITTER * R);
+}
 
 int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, double* d_r2,
                    cudaStream_t st) {
@@ -552,50 +632,68 @@ int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, doubl
 }
 
 template <int M>
-static size_t fit_smem(int R) {
-  return sizeof(double) * ((size_t)M * M + 2 * M + (size_t)GP_WARPS * M * (M + 1) + 3 * (size_t)NNGP_N_JITTER * R);
-}
+static size_t warp_tile_bytes() { return sizeof(double) * (size_t)GP_WARPS * M * (M + 1); }
 
 template <int M>
-static int fit_launch_m(nngp_handle_t h, const FitArgs& A, int nq, cudaStream_t st) {
-  const size_t smem = fit_smem<M>(A.R);
-  if (smem > 227 * 1024) return nngp_fail(h, "fit: shared memory %zu too large (R=%d)", smem, A.R);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_predict_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
+  static int ctas_per_sm = 0;
+  const size_t smem = warp_tile_bytes<M>();
+  if (ctas_per_sm == 0) {
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_predict_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NNGP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gp_fit_predict_kernel<M>,
+                                                               GP_WARPS * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  // persistent grid: every resident warp slot pulls searches from the queue
+  long long blocks = (long long)sms * ctas_per_sm;
+  const long long need = (A.ntasks + GP_WARPS - 1) / GP_WARPS;
+  if (blocks > need) blocks = need;
   ProfScope prof(h, 3, st);
-  gp_fit_predict_kernel<M><<<dim3(A.d, nq), GP_WARPS * 32, smem, st>>>(A);
+  gp_fit_predict_kernel<M><<<(unsigned)blocks, GP_WARPS * 32, smem, st>>>(A);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
 }
 
+#define DISPATCH_CASE(MMV, CALL) else if ((m) <= MMV) { constexpr int MM = MMV; CALL; }
 #define DISPATCH_M(m, CALL)                                                   \
   do {                                                                        \
-    if ((m) <= 12) { constexpr int MM = 12; CALL; }                           \
-    else if ((m) <= 16) { constexpr int MM = 16; CALL; }                      \
-    else if ((m) <= 20) { constexpr int MM = 20; CALL; }                      \
-    else if ((m) <= 24) { constexpr int MM = 24; CALL; }                      \
+    if ((m) <= 6) { constexpr int MM = 6; CALL; }                             \
+    DISPATCH_CASE(8, CALL) DISPATCH_CASE(10, CALL) DISPATCH_CASE(12, CALL)    \
+    DISPATCH_CASE(14, CALL) DISPATCH_CASE(16, CALL) DISPATCH_CASE(18, CALL)   \
+    DISPATCH_CASE(20, CALL) DISPATCH_CASE(22, CALL) DISPATCH_CASE(24, CALL)   \
+    DISPATCH_CASE(26, CALL) DISPATCH_CASE(28, CALL) DISPATCH_CASE(30, CALL)   \
     else { constexpr int MM = 32; CALL; }                                     \
   } while (0)
 
-int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist,
-                          const double* d_r2, int nq, int m, int R, const signed char* d_starts,
+// `ws` = gp_fit_ws_bytes() block whose first part already holds r2 (gp_prep_launch) and whose
+// `done` part is zero (it is left zero by the kernel); `queue` = a zeroed counter.
+int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist, void* ws,
+                          unsigned int* queue, int nq, int m, int R, const signed char* d_starts,
                           double fatol, double xatol, double* d_pred, const double* d_add,
-                          double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt,
-                          int* d_nfev, double* d_fvals, double* d_thetas, cudaStream_t st) {
+                          long long ld_pred, double* d_theta_opt, double* d_jitter_opt,
+                          double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
+                          cudaStream_t st) {
   if (nq <= 0) return 0;
   if (m < 1 || m > NNGP_MAX_NEIGHBOURS) return nngp_fail(h, "fit: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS);
   if (R < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", R);
+  const int d = h->ds_d;
+  const long long ntasks = (long long)nq * d * NNGP_N_JITTER * R;
+  if (ntasks > 0x7fffffffLL) return nngp_fail(h, "fit: %lld searches in one launch (limit 2^31)", ntasks);
+  char* base = (char*)ws;
   FitArgs A;
-  A.idx = d_idx; A.dist = d_dist; A.r2 = d_r2; A.Y = h->ds_y; A.starts = d_starts; A.add = d_add;
+  A.idx = d_idx; A.dist = d_dist; A.Y = h->ds_y; A.starts = d_starts; A.add = d_add;
+  A.r2 = (const double*)base;
+  A.res = (double*)(base + pad256(gp_prep_bytes(nq, m)));
+  A.done = (unsigned int*)(base + gp_fit_done_offset(nq, d, m, R));
+  A.queue = queue;
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
-  A.d = h->ds_d; A.m = m; A.R = R; A.ld_pred = h->ds_d; A.fatol = fatol; A.xatol = xatol;
+  A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
   int rc = 0;
-  DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, nq, st));
+  DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   return rc;
 }
 
@@ -603,13 +701,14 @@ template <int M>
 static int nll_launch_m(nngp_handle_t h, const long long* idx, const double* r2, int nq, int m,
                         int nt, const double* theta, const double* j10, double* out,
                         cudaStream_t st) {
-  const size_t smem = sizeof(double) * ((size_t)M * M + 2 * M + (size_t)GP_WARPS * M * (M + 1));
+  const size_t smem = warp_tile_bytes<M>();
   static bool attr_set = false;
   if (!attr_set) {
-    NNGP_CUDA(h, cudaFuncSetAttribute(gp_nll_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_nll_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gp_nll_kernel<M><<<dim3(h->ds_d, nq), GP_WARPS * 32, smem, st>>>(idx, r2, h->ds_y, h->ds_d, m, nt, theta, j10, out);
+  const int d = h->ds_d;
+  gp_nll_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, r2, h->ds_y, d, m, nq, nt, theta, j10, out);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
@@ -629,14 +728,14 @@ template <int M>
 static int mean_launch_m(nngp_handle_t h, const long long* idx, const double* dist,
                          const double* r2, int nq, int m, const double* theta,
                          const double* jitter, double* pred, cudaStream_t st) {
-  const size_t smem = sizeof(double) * ((size_t)M * M + (size_t)GP_WARPS * M * (M + 1) + (size_t)GP_WARPS * M + M);
+  const size_t smem = warp_tile_bytes<M>();
   static bool attr_set = false;
   if (!attr_set) {
-    NNGP_CUDA(h, cudaFuncSetAttribute(gp_mean_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_mean_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int d = h->ds_d;
-  gp_mean_kernel<M><<<dim3((d + GP_WARPS - 1) / GP_WARPS, nq), GP_WARPS * 32, smem, st>>>(idx, dist, r2, h->ds_y, d, m, theta, jitter, pred);
+  gp_mean_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, dist, r2, h->ds_y, d, m, nq, theta, jitter, pred);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
