@@ -5,12 +5,12 @@
 // and the vector fields ODE.get_vector_field() (systems.py:32-44) with the Normalize affine
 // map (utils.py:14-33) fused into the right-hand side.
 //
-// Arithmetic contract: this file is compiled with -fmad=false and mirrors the reference's
-// NumPy operation order (k_i = h*f(u + sum_j a_ij k_j) accumulated left to right from 0,
-// u += np.sum(b*k) in NumPy's 8-lane pairwise order), so the closed-form ODE systems
-// reproduce the NumPy path bit for bit.  The PDE systems use the 3/5-point periodic stencil
-// form of the reference's dense difference matrices; only the order of that 3/5-term sum
-// differs from the BLAS mat-vec (ulp-level).
+// Arithmetic contract: this file is compiled with -fmad=false.  The closed-form ODE systems
+// mirror the reference's NumPy operation order (k_i = h*f(u + sum_j a_ij k_j) accumulated left to
+// right from 0, u += np.sum(b*k) in NumPy's 8-lane pairwise order) and reproduce the NumPy path
+// bit for bit.  The PDE systems use the 3/5-point periodic stencil form of the reference's dense
+// difference matrices -- already not bit-comparable with a BLAS mat-vec -- and explicit fused
+// multiply-adds in the stage combinations (ulp-level differences, tests: 1e-11 scaled).
 //
 // Layouts: small ODEs (d<=4) one THREAD per slice, everything in registers.  PDE systems one
 // CTA per slice, one thread per grid point, the stage input staged in (double-buffered)
@@ -253,6 +253,27 @@ __device__ __forceinline__ void small_field_n(const SysArgs& A, const double (&m
 template <int S>
 struct SlotOf { static constexpr int value = (S == 1) ? 0 : (S == 2) ? 1 : (S == 4) ? 2 : 3; };
 
+// structural non-zeros of the Butcher matrices of RK.py:30-48 (a term a_ij*k_j with a_ij = 0 adds
+// exactly nothing, so skipping it is bit-identical to the reference's dense accumulation)
+template <int S>
+__host__ __device__ constexpr bool a_nonzero(int i, int j) {
+  if (S == 2) return i == 1 && j == 0;
+  if (S == 4) return j == i - 1;
+  if (S == 11) {
+    if (i <= 3) return true;
+    if (i <= 6) return j != 1;
+    if (i <= 9) return j == 0 || j >= 4;
+    return j >= 4;
+  }
+  return false;
+}
+template <int S>
+__host__ __device__ constexpr bool b_nonzero(int i) {
+  if (S == 2) return i == 1;
+  if (S == 11) return i == 0 || i >= 7;
+  return true;
+}
+
 template <int SYS, int S>
 __global__ void __launch_bounds__(32)
 rk_small_kernel(SysArgs A, int h_mode, long long steps, int n_slices,
@@ -283,10 +304,8 @@ rk_small_kernel(SysArgs A, int h_mode, long long steps, int n_slices,
       for (int c = 0; c < D; c++) {
         double tmp = 0.0;
 #pragma unroll
-        for (int j = 0; j < i; j++) {
-          const double aij = T.a[i * NNGP_MAX_STAGES + j];
-          if (aij != 0.0) tmp = tmp + aij * k[c][j];
-        }
+        for (int j = 0; j < i; j++)
+          if (a_nonzero<S>(i, j)) tmp = tmp + T.a[i * NNGP_MAX_STAGES + j] * k[c][j];
         w[c] = (i == 0) ? u[c] : (u[c] + tmp);
       }
       small_field_n<SYS, D>(A, mn, rg, sc, w, f);
@@ -344,18 +363,12 @@ struct FhnPde {
                        double (&f)[2]) const {
     const double* b1 = buf;
     const double* b2 = buf + npts;
-    double m1 = A.p[2] * b1[pd];
-    m1 = m1 + A.p[2] * b1[pl];
-    m1 = m1 + A.p[1] * v[0];
-    m1 = m1 + A.p[2] * b1[pr];
-    m1 = m1 + A.p[2] * b1[pu];
-    double m2 = A.p[4] * b2[pd];
-    m2 = m2 + A.p[4] * b2[pl];
-    m2 = m2 + A.p[3] * v[1];
-    m2 = m2 + A.p[4] * b2[pr];
-    m2 = m2 + A.p[4] * b2[pu];
+    const double s1 = (b1[pd] + b1[pl]) + (b1[pr] + b1[pu]);
+    const double s2 = (b2[pd] + b2[pl]) + (b2[pr] + b2[pu]);
+    const double m1 = fma(A.p[2], s1, A.p[1] * v[0]);  // a*(DXX+DYY)@u1 as a 5-point stencil
+    const double m2 = fma(A.p[4], s2, A.p[3] * v[1]);
     // U = a*(DXX+DYY)@u1 + u1 - u1**3 - u2 + k ;  V = (1/tau)*(b*(DXX+DYY)@u2 + u1 - u2)
-    f[0] = (((m1 + v[0]) - cube_cr(v[0])) - v[1]) + A.p[5];
+    f[0] = (((m1 + v[0]) - (v[0] * v[0]) * v[0]) - v[1]) + A.p[5];
     f[1] = A.p[6] * ((m2 + v[0]) - v[1]);
   }
 };
@@ -374,16 +387,21 @@ struct BurgersPde {
   __device__ void eval(const SysArgs& A, const double* buf, int p, const double (&v)[1],
                        double (&f)[1]) const {
     const double ul = buf[pl], ur = buf[pr];
-    double lap = A.p[0] * ul;
-    lap = lap + A.p[1] * v[0];
-    lap = lap + A.p[0] * ur;
-    const double adv = (-A.p[2]) * ul + A.p[2] * ur;
-    f[0] = lap - v[0] * adv;  // Dxx@u - u*(Dx@u)
+    const double lap = fma(A.p[0], ul + ur, A.p[1] * v[0]);
+    const double adv = A.p[2] * (ur - ul);
+    f[0] = fma(-v[0], adv, lap);  // Dxx@u - u*(Dx@u)
   }
 };
 
-template <class RHS, int S, int TB>
-__global__ void __launch_bounds__(TB)
+// CTAs per SM the PDE kernel is compiled for: 256-thread CTAs x 4 = all 512 slices of the FHN
+// target resident in one wave on 148 SMs (64 registers per thread)
+template <int TB> struct PdeOcc { static constexpr int value = (TB <= 256) ? 4 : 1; };
+
+// The stage combination and the final update use fused multiply-adds here: the PDE fields are not
+// bit-comparable with the reference anyway (stencil vs dense BLAS mat-vec), and FMA halves the FP64
+// instruction count of the step.
+template <class RHS, int S, int TB, bool NORM>
+__global__ void __launch_bounds__(TB, PdeOcc<TB>::value)
 rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__ t0s,
               const double* __restrict__ t1s, const double* __restrict__ u0, long long ld0,
               double* __restrict__ u1, long long ld1) {
@@ -397,13 +415,14 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
   const long long s = blockIdx.x;
   RHS rhs;
   rhs.setup(A, pp);
-  double u[NC], mn[NC], rg[NC], sc[NC], k[NC][S];
+  double u[NC], mn[NC], hrg[NC], sc[NC], k[NC][S];
 #pragma unroll
   for (int c = 0; c < NC; c++) {
     u[c] = u0[s * ld0 + c * npts + pp];
-    mn[c] = A.normalize ? A.mn[c * npts + pp] : 0.0;
-    rg[c] = A.normalize ? (A.mx[c * npts + pp] - A.mn[c * npts + pp]) : 2.0;
-    sc[c] = 2.0 / rg[c];
+    mn[c] = NORM ? A.mn[c * npts + pp] : 0.0;
+    const double rg = NORM ? (A.mx[c * npts + pp] - A.mn[c * npts + pp]) : 2.0;
+    hrg[c] = 0.5 * rg;
+    sc[c] = 2.0 / rg;
   }
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
@@ -417,26 +436,24 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
       par ^= 1;
 #pragma unroll
       for (int c = 0; c < NC; c++) {
-        double tmp = 0.0;
+        double w = u[c];
 #pragma unroll
-        for (int j = 0; j < i; j++) {
-          const double aij = T.a[i * NNGP_MAX_STAGES + j];
-          if (aij != 0.0) tmp = tmp + aij * k[c][j];
-        }
-        const double w = (i == 0) ? u[c] : (u[c] + tmp);
-        v[c] = A.normalize ? (((w + 1.0) / 2.0) * rg[c] + mn[c]) : w;
+        for (int j = 0; j < i; j++)
+          if (a_nonzero<S>(i, j)) w = fma(T.a[i * NNGP_MAX_STAGES + j], k[c][j], w);
+        v[c] = NORM ? fma(w + 1.0, hrg[c], mn[c]) : w;  // utils.py:24-27
         if (active) buf[c * npts + p] = v[c];
       }
       __syncthreads();
       rhs.eval(A, buf, pp, v, f);
 #pragma unroll
-      for (int c = 0; c < NC; c++) {
-        if (A.normalize) f[c] = f[c] * sc[c];
-        k[c][i] = h * f[c];
-      }
+      for (int c = 0; c < NC; c++) k[c][i] = NORM ? (h * sc[c]) * f[c] : h * f[c];
     }
 #pragma unroll
-    for (int c = 0; c < NC; c++) u[c] = u[c] + numpy_sum_bk<S>(k[c], T.b);
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+      for (int i = 0; i < S; i++)
+        if (b_nonzero<S>(i)) u[c] = fma(T.b[i], k[c][i], u[c]);
+    }
   }
   if (active) {
 #pragma unroll
@@ -502,17 +519,17 @@ static void launch_small(const SysArgs& A, int method, int h_mode, long long ste
   }
 }
 
-template <class RHS, int TB>
+template <class RHS, int TB, bool NORM>
 static void launch_pde_tb(const SysArgs& A, int npts, int method, int h_mode, long long steps,
                           int n, const double* t0, const double* t1, const double* u0,
                           long long ld0, double* u1, long long ld1, cudaStream_t st) {
   const int threads = ((npts + 31) / 32) * 32;
   const size_t smem = 2 * sizeof(double) * RHS::NC * npts;
   switch (method) {
-    case 1: rk_pde_kernel<RHS, 1, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 2: rk_pde_kernel<RHS, 2, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 4: rk_pde_kernel<RHS, 4, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    default: rk_pde_kernel<RHS, 11, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 1: rk_pde_kernel<RHS, 1, TB, NORM><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 2: rk_pde_kernel<RHS, 2, TB, NORM><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 4: rk_pde_kernel<RHS, 4, TB, NORM><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    default: rk_pde_kernel<RHS, 11, TB, NORM><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
   }
 }
 
@@ -520,10 +537,13 @@ template <class RHS>
 static void launch_pde(const SysArgs& A, int npts, int method, int h_mode, long long steps,
                        int n, const double* t0, const double* t1, const double* u0,
                        long long ld0, double* u1, long long ld1, cudaStream_t st) {
-  if (npts <= 256)
-    launch_pde_tb<RHS, 256>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
-  else
-    launch_pde_tb<RHS, 1024>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+  if (npts <= 256) {
+    if (A.normalize) launch_pde_tb<RHS, 256, true>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+    else launch_pde_tb<RHS, 256, false>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+  } else {
+    if (A.normalize) launch_pde_tb<RHS, 1024, true>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+    else launch_pde_tb<RHS, 1024, false>(A, npts, method, h_mode, steps, n, t0, t1, u0, ld0, u1, ld1, st);
+  }
 }
 
 static int check_system(nngp_handle_t h, const SystemDesc& s, int* npts) {

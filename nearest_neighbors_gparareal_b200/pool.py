@@ -43,19 +43,33 @@ class CudaPool():
                 return buf[:n].cpu().numpy()
         return batch(t0, t1, u0)
 
-    def map(self, fn, *iterables, chunksize=None):
+    @staticmethod
+    def _which(fn):
+        """(owner, 'F'|'G', timed) when fn is run_F / run_F_timed / run_G / run_G_timed of a solver that
+        can batch; identified by function identity, because the reference's timing decorator
+        (solver.py:21-27) does not preserve __name__."""
         owner = getattr(fn, "__self__", None)
-        name = getattr(fn, "__name__", "")
-        if owner is not None and hasattr(owner, "run_F_batch") and name in (
-                "run_F_timed", "run_F", "run_G_timed", "run_G"):
+        func = getattr(fn, "__func__", None)
+        if owner is None or func is None or not hasattr(owner, "run_F_batch"):
+            return None
+        for name, kind, timed in (("run_F_timed", "F", True), ("run_F", "F", False),
+                                  ("run_G_timed", "G", True), ("run_G", "G", False)):
+            if getattr(type(owner), name, None) is func:
+                return owner, kind, timed
+        return None
+
+    def map(self, fn, *iterables, chunksize=None):
+        hit = self._which(fn)
+        if hit is not None:
+            owner, kind, timed = hit
             t0, t1, u0 = [list(it) for it in iterables]
             if len(t0) == 0:
                 return []
             s = time.time()
-            batch = owner.run_F_batch if "F" in name else owner.run_G_batch
+            batch = owner.run_F_batch if kind == "F" else owner.run_G_batch
             u1 = self._batch(batch, np.asarray(t0, dtype=float), np.asarray(t1, dtype=float), np.stack(u0))
             secs = (time.time() - s) / len(t0)
-            if name.endswith("_timed"):
+            if timed:
                 return [(u1[i], secs) for i in range(len(t0))]
             return [u1[i] for i in range(len(t0))]
         return map(fn, *iterables)
