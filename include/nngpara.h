@@ -143,9 +143,10 @@ int nngp_append_iteration(nngp_handle_t h, const double* d_u_cur, const double* 
 int nngp_rowwise_maxabs_diff(nngp_handle_t h, const double* d_a, const double* d_b, int rows,
                              int d, double* d_err, void* stream);
 
-/* test hook: the device exp(-|x|) and 1/sqrt(|x|) used inside the GP kernels, for n values */
-int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rsqrt,
-                       void* stream);
+/* test hook: the device exp(-|x|), 1/|x| and -- when d_exp10 (2n doubles) is not NULL -- [10**x | log|x| + 3 ln 2]
+ * used inside the GP kernels */
+int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rcp,
+                       double* d_exp10, void* stream);
 
 /* counters of kernel launches issued through this handle (bench.py: gpu_launches) */
 long long nngp_launch_count(nngp_handle_t h);

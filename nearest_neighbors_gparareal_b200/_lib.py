@@ -50,7 +50,7 @@ SIGNATURES = {
     "nngp_sweep": (ci, [vp, ci, ci, ci, cll, vp, ci, ci, ci, ci, vp, cd, cd, vp, vp, ci, vp]),
     "nngp_append_iteration": (ci, [vp, vp, vp, vp, ci, ci, ci, vp]),
     "nngp_rowwise_maxabs_diff": (ci, [vp, vp, vp, ci, ci, vp, vp]),
-    "nngp_selftest_math": (ci, [vp, vp, ci, vp, vp, vp]),
+    "nngp_selftest_math": (ci, [vp, vp, ci, vp, vp, vp, vp]),
     "nngp_launch_count": (cll, [vp]),
     "nngp_counters": (ci, [vp, c_ll_p, c_ll_p, ci]),
     "nngp_profile_enable": (ci, [vp, ci]),
@@ -254,8 +254,9 @@ class Handle:
     def rowwise_maxabs_diff(self, d_a, d_b, rows, d, d_err, stream=None):
         self.check(self.lib.nngp_rowwise_maxabs_diff(self.h, _ptr(d_a), _ptr(d_b), int(rows), int(d), _ptr(d_err), stream))
 
-    def selftest_math(self, d_x, n, d_exp, d_rsqrt, stream=None):
-        self.check(self.lib.nngp_selftest_math(self.h, _ptr(d_x), int(n), _ptr(d_exp), _ptr(d_rsqrt), stream))
+    def selftest_math(self, d_x, n, d_exp, d_rcp, d_exp10=None, stream=None):
+        self.check(self.lib.nngp_selftest_math(self.h, _ptr(d_x), int(n), _ptr(d_exp), _ptr(d_rcp),
+                                               _ptr(d_exp10) if d_exp10 is not None else None, stream))
 
     def synchronize(self, stream=None):
         self.check(self.lib.nngp_synchronize(self.h, stream))

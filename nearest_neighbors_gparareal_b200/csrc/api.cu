@@ -431,13 +431,16 @@ int nngp_knn_host(nngp_handle_t h, const double* q, int nq, int m, long long n_r
 
 // ---- GP fit / predict ------------------------------------------------------------------
 // workspace layout for a fit on nq queries: [knn distances nq*n | fit block (r2 | results | done)]
-static int fit_workspace(nngp_handle_t h, int nq, long long n, int m, int R, void** knn_ws, void** fit_ws) {
+static int fit_workspace(nngp_handle_t h, int nq, long long n, int m, int R, void** knn_ws, void** fit_ws,
+                         int** order = nullptr) {
   const size_t bk = Carver::pad(knn_workspace_bytes(nq, n, m));
   const size_t bf = Carver::pad(gp_fit_ws_bytes(nq, h->ds_d, m, R));
-  char* ws = (char*)nngp_workspace(h, bk + bf);
-  if (!ws) return nngp_fail(h, "fit: out of device memory (workspace %zu bytes)", bk + bf);
+  const size_t bo = Carver::pad(sizeof(int) * (size_t)nq * h->ds_d * NNGP_N_JITTER * R);
+  char* ws = (char*)nngp_workspace(h, bk + bf + bo);
+  if (!ws) return nngp_fail(h, "fit: out of device memory (workspace %zu bytes)", bk + bf + bo);
   *knn_ws = ws;
   *fit_ws = ws + bk;
+  if (order) *order = (int*)(ws + bk + bf);
   return 0;
 }
 
@@ -449,11 +452,13 @@ int nngp_fit_predict(nngp_handle_t h, const double* d_q, const long long* d_idx,
   (void)d_q;
   if (n_restarts < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", n_restarts);
   void *kws, *fws;
-  if (int rc = fit_workspace(h, nq, h->ds_rows, m, n_restarts, &kws, &fws)) return rc;
+  int* order;
+  if (int rc = fit_workspace(h, nq, h->ds_rows, m, n_restarts, &kws, &fws, &order)) return rc;
   cudaStream_t st = as_stream(stream);
   if (int rc = ensure_done_zero(h, fws, nq, h->ds_d, m, n_restarts, st)) return rc;
   if (int rc = gp_prep_launch(h, d_idx, nq, m, (double*)fws, st)) return rc;
-  return gp_fit_predict_launch(h, d_idx, d_dist, fws, next_queue(h, st), nq, m, n_restarts, d_starts, fatol,
+  if (int rc = gp_order_launch(h, d_starts, nq, h->ds_d * NNGP_N_JITTER * n_restarts, 1, order, st)) return rc;
+  return gp_fit_predict_launch(h, d_idx, d_dist, fws, next_queue(h, st), order, nq, m, n_restarts, d_starts, fatol,
                                xatol, d_pred, nullptr, h->ds_d, d_theta_opt, d_jitter_opt, d_fval_opt, d_nfev,
                                d_fvals, d_thetas, st);
 }
@@ -505,11 +510,13 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
   NNGP_CUDA(h, cudaMemcpyAsync(gst, starts, ntask * 2, cudaMemcpyHostToDevice, st));
   if (R < 1) return nngp_fail(h, "predict: n_restarts=%d < 1", R);
   void *kws, *fws;
-  if (int rc = fit_workspace(h, nq, n, m, R, &kws, &fws)) return rc;
+  int* order;
+  if (int rc = fit_workspace(h, nq, n, m, R, &kws, &fws, &order)) return rc;
   if (int rc = ensure_done_zero(h, fws, nq, d, m, R, st)) return rc;
   if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
   if (int rc = gp_prep_launch(h, gidx, nq, m, (double*)fws, st)) return rc;
-  if (int rc = gp_fit_predict_launch(h, gidx, gdist, fws, next_queue(h, st), nq, m, R, gst, fatol, xatol,
+  if (int rc = gp_order_launch(h, gst, nq, d * NNGP_N_JITTER * R, 1, order, st)) return rc;
+  if (int rc = gp_fit_predict_launch(h, gidx, gdist, fws, next_queue(h, st), order, nq, m, R, gst, fatol, xatol,
                                      (double*)(dev + o_pred), nullptr, d,
                                      theta_opt ? (double*)(dev + o_th) : nullptr,
                                      jitter_opt ? (double*)(dev + o_jit) : nullptr,
@@ -545,13 +552,18 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
   const size_t bk = Carver::pad(knn_workspace_bytes(1, n, m));
   const size_t bf = Carver::pad(gp_fit_ws_bytes(1, d, m, n_restarts));
   const size_t bi = Carver::pad(sizeof(long long) * m), bd = Carver::pad(sizeof(double) * m);
-  char* ws = (char*)nngp_workspace(h, bk + bf + bi + bd);
+  const int seg_len = d * NNGP_N_JITTER * n_restarts;
+  const size_t bo = Carver::pad(sizeof(int) * (size_t)seg_len * (size_t)(N - I));
+  char* ws = (char*)nngp_workspace(h, bk + bf + bi + bd + bo);
   if (!ws) return nngp_fail(h, "sweep: out of device memory");
   void* kws = ws;
   void* fws = ws + bk;
   long long* idx = (long long*)(ws + bk + bf);
   double* dist = (double*)(ws + bk + bf + bi);
+  int* order = (int*)(ws + bk + bf + bi + bd);
   if (int rc = ensure_done_zero(h, fws, 1, d, m, n_restarts, st)) return rc;
+  // queue order of every predict of the sweep in one launch (the starts are all known up front)
+  if (int rc = gp_order_launch(h, d_starts, N - I, seg_len, 0, order, st)) return rc;
   const size_t per_predict = (size_t)d * NNGP_N_JITTER * n_restarts * 2;
   for (int i = I; i < N; i++) {
     double* ui = d_u_next + (long long)i * d;
@@ -560,17 +572,17 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
     if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
     if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
     if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
-    if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), 1, m, n_restarts,
-                                       d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn, d,
+    if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), order + (size_t)(i - I) * seg_len, 1, m,
+                                       n_restarts, d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn, d,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st))
       return rc;
   }
   return 0;
 }
 
-int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rsqrt,
-                       void* stream) {
-  return selftest_math_launch(h, d_x, n, d_exp_neg, d_rsqrt, as_stream(stream));
+int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rcp,
+                       double* d_exp10, void* stream) {
+  return selftest_math_launch(h, d_x, n, d_exp_neg, d_rcp, d_exp10, as_stream(stream));
 }
 
 // ---- roofline micro-benchmarks ---------------------------------------------------------

@@ -115,8 +115,10 @@ size_t gp_fit_ws_bytes(int nq, int d, int m, int R);      // [r2 | per-search re
 size_t gp_fit_done_offset(int nq, int d, int m, int R);   // byte offset of the done counters
 int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, double* d_r2,
                    cudaStream_t st);
+int gp_order_launch(nngp_handle_t h, const signed char* d_starts, int nseg, int seg_len, int global_ids,
+                    int* d_order, cudaStream_t st);
 int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist, void* ws,
-                          unsigned int* queue, int nq, int m, int R, const signed char* d_starts,
+                          unsigned int* queue, const int* order, int nq, int m, int R, const signed char* d_starts,
                           double fatol, double xatol, double* d_pred, const double* d_add,
                           long long ld_pred, double* d_theta_opt, double* d_jitter_opt,
                           double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
@@ -128,6 +130,6 @@ int gp_mean_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist
                    const double* d_r2, int nq, int m, const double* d_theta,
                    const double* d_jitter, double* d_pred, cudaStream_t st);
 
-int selftest_math_launch(nngp_handle_t h, const double* d_x, int n, double* d_exp, double* d_rsqrt,
-                         cudaStream_t st);
+int selftest_math_launch(nngp_handle_t h, const double* d_x, int n, double* d_exp, double* d_rcp,
+                         double* d_exp10, cudaStream_t st);
 

@@ -133,6 +133,33 @@ def test_device_exp_and_rsqrt_accuracy(handle):
     nan = torch.tensor([float('nan')], dtype=torch.float64, device=dev)
     handle.selftest_math(nan, 1, te, tr)
     assert np.isnan(te.cpu().numpy()[0])
+    # 10**x of the hyper-parameter transforms (models.py:145-148): within 2 ulp of numpy's pow on the range a
+    # search can reach, library behaviour (inf / 0 / NaN) outside
+    xs = np.concatenate([rng.uniform(-300, 300, 40000), rng.uniform(-12, 4, 20000), np.arange(-20.0, 3.0),
+                         [-400.0, 400.0, 308.2, -323.0, np.nan]])
+    tx = torch.from_numpy(xs).to(dev)
+    te, tr = torch.empty_like(tx), torch.empty_like(tx)
+    t10 = torch.empty(2 * xs.size, dtype=torch.float64, device=dev)  # [10**x | log|x| + 3 ln 2]
+    handle.selftest_math(tx, xs.size, te, tr, t10)
+    g10 = t10.cpu().numpy()[:xs.size]
+    with np.errstate(all="ignore"):
+        want10 = 10.0 ** xs
+    fin = np.isfinite(want10) & (want10 > 1e-300)
+    assert np.max(np.abs(g10[fin] - want10[fin]) / np.spacing(want10[fin])) <= 2.0
+    assert g10[xs == 400.0][0] == np.inf and g10[xs == -400.0][0] == 0.0 and np.isnan(g10[-1])
+    # log of the determinant accumulator: log(x) + k ln2 within 1 ulp
+    xl = np.concatenate([rng.uniform(1.0, 2.0 ** 21, 20000), 10.0 ** rng.uniform(-300, 300, 20000), [1.0, 2.0, np.sqrt(2)]])
+    tx = torch.from_numpy(xl).to(dev)
+    te, tr = torch.empty_like(tx), torch.empty_like(tx)
+    t10 = torch.empty(2 * xl.size, dtype=torch.float64, device=dev)
+    handle.selftest_math(tx, xl.size, te, tr, t10)
+    gl = t10.cpu().numpy()[xl.size:]
+    from decimal import Decimal, getcontext
+    getcontext().prec = 40
+    ln2 = Decimal(2).ln()
+    sub = rng.permutation(xl.size)[:3000]
+    wantl = np.array([float(Decimal(float(v)).ln() + 3 * ln2) for v in xl[sub]])
+    assert np.max(np.abs(gl[sub] - wantl) / np.spacing(np.abs(wantl))) <= 1.0
 
 
 def make_dataset(rng, n, d):
