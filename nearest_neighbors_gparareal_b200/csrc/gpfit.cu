@@ -262,10 +262,10 @@ struct Tri {
 // which entries of the strict lower triangle a lane computes: e = lane + 32 t -> (i > j)
 template <int M>
 struct PairSlots {
-  int oij[Tri<M>::NP];  // i*LD + j, or -1 for an empty slot
+  int oij[Tri<M>::NP];  // i*LD + j; an empty slot points at the unused diagonal element 0
   int oji[Tri<M>::NP];
   double r2[Tri<M>::NP];
-  bool pad[Tri<M>::NP];  // entry touches a padding row (m <= i < M): stored as 0
+  bool pad[Tri<M>::NP];  // entry touches a padding row (m <= i < M) or slot empty: stored as 0
 };
 
 template <int M>
@@ -278,9 +278,10 @@ __device__ __forceinline__ void pair_slots_init(PairSlots<M>& P, int lane, int m
     while ((i + 1) * i / 2 <= e) i++;
     const int j = e - i * (i - 1) / 2;
     const bool valid = e < Tri<M>::NPAIR;
-    P.oij[t] = valid ? i * Tri<M>::LD + j : -1;
-    P.oji[t] = valid ? j * Tri<M>::LD + i : -1;
-    P.pad[t] = valid && (i >= m);
+    // an empty slot stores (zero) to the unused diagonal element K_00 instead of branching
+    P.oij[t] = valid ? i * Tri<M>::LD + j : 0;
+    P.oji[t] = valid ? j * Tri<M>::LD + i : 0;
+    P.pad[t] = !valid || (i >= m);
     P.r2[t] = 0.0;
   }
 }
@@ -291,7 +292,7 @@ __device__ __forceinline__ void pair_slots_load(PairSlots<M>& P, const double* _
 #pragma unroll
   for (int t = 0; t < Tri<M>::NP; t++) {
     double v = 0.0;
-    if (P.oij[t] >= 0 && !P.pad[t]) {
+    if (!P.pad[t]) {
       const int i = P.oij[t] / Tri<M>::LD, j = P.oij[t] - i * Tri<M>::LD;
       v = __ldg(r2 + i * m + j);
     }
@@ -344,12 +345,10 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   }
   const double dd0 = amp * v[NP] + jit10;  // K_rr = amp*exp(c*0) + 10**jitter
 #pragma unroll
-  for (int t = 0; t < NP; t++) {
-    if (P.oij[t] >= 0) {
-      const double e = P.pad[t] ? 0.0 : amp * v[t];
-      Kt[P.oij[t]] = e;
-      Kt[P.oji[t]] = e;
-    }
+  for (int t = 0; t < NP; t++) {  // unconditional stores: the exponentials above stay interleaved
+    const double e = P.pad[t] ? 0.0 : amp * v[t];
+    Kt[P.oij[t]] = e;
+    Kt[P.oji[t]] = e;
   }
   __syncwarp();
   const bool rowvalid = lane < m;
