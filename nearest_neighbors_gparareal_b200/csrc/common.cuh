@@ -28,6 +28,7 @@ struct SysArgs {
   int d;
   int normalize;
   double p[NNGP_MAX_PARAMS];
+  double q[4];  // derived parameters (rk.cu)
   const double* mn;
   const double* mx;
 };
