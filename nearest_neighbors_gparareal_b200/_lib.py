@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnngpara.so")
+LIB_PATH = os.environ.get("NNGPARA_LIB") or os.path.join(_PKG, "libnngpara.so")  # override: kernel-variant experiments
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_ll_p = ctypes.POINTER(ctypes.c_longlong)

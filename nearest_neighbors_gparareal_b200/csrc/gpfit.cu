@@ -263,7 +263,6 @@ struct Tri {
 template <int M>
 struct PairSlots {
   int oij[Tri<M>::NP];  // i*LD + j; an empty slot points at the unused diagonal element 0
-  int oji[Tri<M>::NP];
   double r2[Tri<M>::NP];
   bool pad[Tri<M>::NP];  // entry touches a padding row (m <= i < M) or slot empty: stored as 0
 };
@@ -280,7 +279,6 @@ __device__ __forceinline__ void pair_slots_init(PairSlots<M>& P, int lane, int m
     const bool valid = e < Tri<M>::NPAIR;
     // an empty slot stores (zero) to the unused diagonal element K_00 instead of branching
     P.oij[t] = valid ? i * Tri<M>::LD + j : 0;
-    P.oji[t] = valid ? j * Tri<M>::LD + i : 0;
     P.pad[t] = !valid || (i >= m);
     P.r2[t] = 0.0;
   }
@@ -343,12 +341,18 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       for (int t = 0; t < G2; t++) v[G + t] = oa[t];
     }
   }
-  const double dd0 = amp * v[NP] + jit10;  // K_rr = amp*exp(c*0) + 10**jitter
+  // The matrix is factorised as K' = 2^-e0 K with e0 = the larger binary exponent of amp and jitter
+  // (an exact scaling: every pivot is scaled by the same power of two), so that the product of up to
+  // 16 pivots, each in (4 ulp, 4) after scaling, stays a normal number and log det K needs no
+  // per-pivot exponent bookkeeping.
+  const int e0 = min(1022, max((__double2hiint(amp) >> 20) & 0x7ff, (__double2hiint(jit10) >> 20) & 0x7ff) - 1023);
+  const double sc = __hiloint2double((1023 - e0) << 20, 0);
+  const double amp_s = amp * sc;
+  const double dd0 = fma(amp_s, v[NP], jit10 * sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
 #pragma unroll
   for (int t = 0; t < NP; t++) {  // unconditional stores: the exponentials above stay interleaved
-    const double e = P.pad[t] ? 0.0 : amp * v[t];
-    Kt[P.oij[t]] = e;
-    Kt[P.oji[t]] = e;
+    // only the lower triangle is stored: lane r never uses the entries right of its diagonal
+    Kt[P.oij[t]] = P.pad[t] ? 0.0 : amp_s * v[t];
   }
   __syncwarp();
   const bool rowvalid = lane < m;
@@ -392,9 +396,8 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
   const double pmin = dd0 * 8.8817841970012523e-16;
   double z = rowvalid ? y : 0.0;
-  double quad = 0.0, prod = 1.0;
+  double quad = 0.0, prod0 = 1.0, prod1 = 1.0;
   double inv_own = 1.0, w_own = 0.0;  // ALPHA: 1/d_r and (L'^-1 y)_r of the own row
-  int esum = 0;
   bool ok = true;
   double u[M];
   double p = shfl(dd, 0), zk = shfl(z, 0);
@@ -425,11 +428,10 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
       if (k + 2 < M) load_col(k + 1, u);
     }
-    if (!ALPHA && k < m) {  // rows that are real (not padding); warp-uniform, off the critical path
+    if (!ALPHA) {  // off the critical path; a padding row has z = 0 and is left out of the determinant
       quad = fma(zkk * zkk, ip, quad);
-      const int hi = __double2hiint(pk);
-      esum += (hi >> 20) - 1023;
-      prod = prod * __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pk));
+      const double pe = (k < m) ? pk : 1.0;
+      if (k < M / 2) prod0 = prod0 * pe; else prod1 = prod1 * pe;
     }
   }
   GpOut o;
@@ -438,8 +440,13 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   o.ok = ok;
   if (!ALPHA) {
     __syncwarp();  // the next evaluation overwrites the tile
-    // -(-0.5*y@alpha - sum(log(diag L)) - (N/2) log(2 pi)),  sum log L_rr = 0.5 log det K
-    const double res = fma(0.5, quad + log_pos_plus(prod, esum), hml);
+    // -(-0.5*y@alpha - sum(log(diag L)) - (N/2) log(2 pi)),  sum log L_rr = 0.5 log det K,
+    // log det K = log(prod0 prod1) + m e0 ln 2,  y^T K^-1 y = 2^-e0 sum z_k^2 / d'_k
+    const int h0 = __double2hiint(prod0), h1 = __double2hiint(prod1);
+    const double m0 = __hiloint2double((h0 & 0x000fffff) | 0x3ff00000, __double2loint(prod0));
+    const double m1 = __hiloint2double((h1 & 0x000fffff) | 0x3ff00000, __double2loint(prod1));
+    const int esum = (h0 >> 20) + (h1 >> 20) - 2046 + m * e0;
+    const double res = fma(0.5, fma(quad, sc, log_pos_plus(m0 * m1, esum)), hml);
     o.val = (ok && res == res) ? res : dinf();
     return o;
   }
@@ -457,7 +464,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     vb = fma(-a[r], ar, vb);  // meaningful for lane < r only
   }
   __syncwarp();
-  o.val = alpha;
+  o.val = alpha * sc;  // K^-1 = 2^-e0 K'^-1
   return o;
 }
 
@@ -645,7 +652,10 @@ __device__ __noinline__ double posterior_mean(double th0, double th1, double jit
 }
 
 // registers per thread: 4-warp CTAs, K CTAs per SM
-template <int M> struct FitOcc { static constexpr int value = (M <= 12) ? 4 : ((M <= 20) ? 3 : 2); };
+#ifndef FIT_OCC20
+#define FIT_OCC20 2
+#endif
+template <int M> struct FitOcc { static constexpr int value = (M <= 12) ? 4 : ((M <= 20) ? FIT_OCC20 : 2); };
 
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32, FitOcc<M>::value)
