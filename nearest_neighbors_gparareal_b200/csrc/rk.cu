@@ -18,6 +18,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 struct Tableau {
   int S;
@@ -486,6 +487,121 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// FHN, identity normalisation, even d_x: one thread owns a 2x2 block of grid points (both fields).
+// ncu (profiles/r01/rk_r1d.summary.csv) shows rk_pde_kernel bound by the shared-memory pipe
+// (8 neighbour loads + 2 stores per point and stage); with 2x2 blocks half of the neighbours are the
+// thread's own registers and the vertical ones come as aligned 16-byte pairs: 12 instead of 20
+// shared-memory accesses per point pair, and 4x fewer threads per barrier.  Per-point arithmetic and
+// summation order are those of FhnPde::eval_k, so both kernels return identical bits.
+// ---------------------------------------------------------------------------------------
+template <int S, int TB>
+__global__ void __launch_bounds__(TB, (TB <= 64) ? 4 : 1)
+rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__ t0s,
+                   const double* __restrict__ t1s, const double* __restrict__ u0, long long ld0,
+                   double* __restrict__ u1, long long ld1) {
+  extern __shared__ double sm[];
+  const Tableau& T = c_tab[SlotOf<S>::value];
+  const int dx = (int)A.p[0], npts = dx * dx, hx = dx >> 1, ntile = hx * hx;
+  const bool active = (int)threadIdx.x < ntile;
+  const int tt = active ? threadIdx.x : 0;
+  const int ix0 = 2 * (tt % hx), iy0 = 2 * (tt / hx);
+  const int o00 = iy0 * dx + ix0, o10 = o00 + dx;
+  const int oup = ((iy0 == 0 ? dx : iy0) - 1) * dx + ix0;      // row iy0-1, columns ix0, ix0+1
+  const int odn = ((iy0 + 2 == dx) ? 0 : iy0 + 2) * dx + ix0;  // row iy0+2
+  const int xl = (ix0 == 0 ? dx : ix0) - 1, xr = (ix0 + 2 == dx) ? 0 : ix0 + 2;
+  const int ol0 = iy0 * dx + xl, ol1 = ol0 + dx, or0 = iy0 * dx + xr, or1 = or0 + dx;
+  const long long s = blockIdx.x;
+  double u[2][4], k[2][4][S];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const double* src = u0 + s * ld0 + c * npts;
+    u[c][0] = src[o00];
+    u[c][1] = src[o00 + 1];
+    u[c][2] = src[o10];
+    u[c][3] = src[o10 + 1];
+  }
+  const double t0 = t0s[s], t1 = t1s[s];
+  const double step = (t1 - t0) / (double)steps;
+  int par = 0;
+  for (long long n = 0; n < steps; n++) {
+    const double h = step_size(h_mode, t0, t1, step, n, steps);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      double* buf = sm + par * (2 * npts);
+      par ^= 1;
+      double w[2][4], sn[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          double x = u[c][q];
+#pragma unroll
+          for (int j = 0; j < i; j++)
+            if (a_nonzero<S>(i, j)) x = fma(T.a[i * NNGP_MAX_STAGES + j], k[c][q][j], x);
+          w[c][q] = x;
+        }
+        if (active) {
+          *reinterpret_cast<double2*>(buf + c * npts + o00) = make_double2(w[c][0], w[c][1]);
+          *reinterpret_cast<double2*>(buf + c * npts + o10) = make_double2(w[c][2], w[c][3]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const double* b = buf + c * npts;
+        const double2 up = *reinterpret_cast<const double2*>(b + oup);
+        const double2 dn = *reinterpret_cast<const double2*>(b + odn);
+        const double l0 = b[ol0], l1 = b[ol1], r0 = b[or0], r1 = b[or1];
+        // (v[iy-1] + v[ix-1]) + (v[ix+1] + v[iy+1]) as in FhnPde::eval_k
+        sn[c][0] = (up.x + l0) + (w[c][1] + w[c][2]);
+        sn[c][1] = (up.y + w[c][0]) + (r0 + w[c][3]);
+        sn[c][2] = (w[c][0] + l1) + (w[c][3] + dn.x);
+        sn[c][3] = (w[c][1] + w[c][2]) + (r1 + dn.y);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double v0 = w[0][q], v1 = w[1][q];
+        const double e1 = fma(-v0, v0, A.q[0]);
+        const double e2 = A.p[5] - v1;
+        k[0][q][i] = h * fma(A.p[2], sn[0][q], fma(v0, e1, e2));
+        k[1][q][i] = h * fma(A.q[1], sn[1][q], fma(A.q[2], v1, A.p[6] * v0));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int i = 0; i < S; i++)
+          if (b_nonzero<S>(i)) u[c][q] = fma(T.b[i], k[c][q][i], u[c][q]);
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      double* dst = u1 + s * ld1 + c * npts;
+      dst[o00] = u[c][0];
+      dst[o00 + 1] = u[c][1];
+      dst[o10] = u[c][2];
+      dst[o10 + 1] = u[c][3];
+    }
+  }
+}
+
+template <int TB>
+static void launch_fhn_tile(const SysArgs& A, int npts, int method, int h_mode, long long steps, int n,
+                            const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
+                            long long ld1, cudaStream_t st) {
+  const int threads = ((npts / 4 + 31) / 32) * 32;
+  const size_t smem = 2 * sizeof(double) * 2 * npts;
+  switch (method) {
+    case 1: rk_fhn_tile_kernel<1, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 2: rk_fhn_tile_kernel<2, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 4: rk_fhn_tile_kernel<4, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    default: rk_fhn_tile_kernel<11, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+  }
+}
+
 template <class RHS>
 __global__ void rhs_pde_kernel(SysArgs A, const double* __restrict__ uin,
                                double* __restrict__ out) {
@@ -626,9 +742,18 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
     case NNGP_SYS_BRUSSELATOR: SMALL(NNGP_SYS_BRUSSELATOR); break;
     case NNGP_SYS_LORENZ: SMALL(NNGP_SYS_LORENZ); break;
     case NNGP_SYS_THOMAS: SMALL(NNGP_SYS_THOMAS); break;
-    case NNGP_SYS_FHN_PDE:
-      launch_pde<FhnPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+    case NNGP_SYS_FHN_PDE: {
+      const int dx = (int)A.p[0];
+      if (!A.normalize && (dx & 1) == 0 && dx >= 4 && getenv("NNGP_RK_NO_TILE") == nullptr) {
+        if (npts / 4 <= 64)
+          launch_fhn_tile<64>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+        else
+          launch_fhn_tile<256>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+      } else {
+        launch_pde<FhnPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+      }
       break;
+    }
     case NNGP_SYS_BURGERS:
       launch_pde<BurgersPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
       break;

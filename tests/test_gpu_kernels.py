@@ -100,6 +100,31 @@ def test_rk_many_slices_both_step_conventions_vs_oracle():
     assert np.array_equal(sp.run_F(0.0, 0.5, o.u0), u)
 
 
+@pytest.mark.parametrize("d_x", [4, 6, 16, 18])
+def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
+    """the 2x2-points-per-thread FHN kernel (csrc/rk.cu rk_fhn_tile_kernel) returns the bits of the
+    one-point-per-thread kernel (NNGP_RK_NO_TILE selects the latter), all RK methods, and both agree with
+    the NumPy oracle to 1e-12 scaled"""
+    import os
+    rng = np.random.default_rng(d_x)
+    o, ode = osys.FHN_PDE(d_x=d_x), nn.FHN_PDE(d_x=d_x)
+    n = 7
+    u0 = o.u0[None, :] + 0.01 * rng.standard_normal((n, 2 * d_x * d_x))
+    t0 = np.arange(n) * 0.5
+    t1 = t0 + 0.7
+    for F, steps in (('RK8', 23), ('RK4', 11), ('RK2', 6), ('RK1', 5)):
+        s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=steps, F=F, G='RK4')
+        got = s.run_F_batch(t0, t1, u0)
+        os.environ["NNGP_RK_NO_TILE"] = "1"
+        try:
+            ref = s.run_F_batch(t0, t1, u0)
+        finally:
+            del os.environ["NNGP_RK_NO_TILE"]
+        assert np.array_equal(got, ref), F
+        want = np.stack([ork.rk_last(o.f, F, t0[i], t1[i], steps, u0[i]) for i in range(n)])
+        assert scaled_err(got, want) < 1e-12, F
+
+
 def test_rk_errors(handle):
     ode = nn.Burgers(d_x=2000, normalization='-11')
     s = nn.CudaSolverRK(ode.get_vector_field(), Ng=1, Nf=1, F='RK4', G='RK1')
