@@ -138,7 +138,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    samples, cores, n_dims = cpu_sample(args, n_dims_per_core=2, n_steps=args.steps, warm=min(args.warmup, 1))
+    samples, cores, n_dims = cpu_sample(args, n_dims_per_core=1 << 20, n_steps=args.steps, warm=min(args.warmup, 1))
     t_iter = float(np.mean([r["t_iter"] for r in samples]))
     d = 2 * args.dx * args.dx
     sample = (f"per step: one predict restricted to {n_dims} of {d} output dims ({n_dims*9} Nelder-Mead searches) "
@@ -202,6 +202,8 @@ def main():
     starts = torch.from_numpy(starts_host).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    fine_events = []
+
     def step():
         st["I"] = 0
         st["u_cur"].copy_(u0_cur)
@@ -209,7 +211,11 @@ def main():
         st["u_next"].copy_(u0_cur)
         st["uG_next"].copy_(uG0_cur)
         h.dataset_reset()
-        par.device_fine_step(st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        par.device_fine_step(st)  # the batched RK8 launch on torch's current stream (+ the all-gather for N>1)
+        e1.record()
+        fine_events.append((e0, e1))
         par.device_sweep(st, 0, starts=starts)
         return par.device_errors(st)  # the one device->host read of an iteration (N+1 doubles)
 
@@ -225,6 +231,7 @@ def main():
     h.profile_read(reset=True)
     h.profile_enable(True)
     launches0 = h.launch_count()
+    fine_events.clear()
     sync_all()
     clocks = ClockSampler(local)
     clocks.start()
@@ -246,28 +253,41 @@ def main():
     nm_runs, nll_evals = h.counters(reset=True)
     launches = (h.launch_count() - launches0) // args.steps
 
-    # ---- roofline of the dominant kernel (GP fit: FP64 pipe) --------------------------------------
+    # ---- rooflines of the two kernels that share the step (fine propagator, GP fit): FP64 pipe ------
     fp64_peak = h.bench_fp64(20000)
+    peak_src = ("FP64 FMA micro-benchmark run in this process (nngp_bench_fp64); MEASURED_PEAKS.json has no FP64 "
+                "entry; the bound is FP64 (neither HBM nor tensor cores: all state is register/shared-memory resident)")
     fit_ms, fit_n = prof["gp_fit"]
-    rk_ms, rk_n = prof["rk"]
     flops_fit = nll_evals * nll_flops(m)
     fit_tf = flops_fit / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0
-    roofline = {"kernel": "gp_fit_predict_kernel", "bound": "fp64", "achieved": fit_tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": fit_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                "peak_source": "FP64 FMA micro-benchmark run in this process (nngp_bench_fp64); "
-                               "MEASURED_PEAKS.json has no FP64 entry",
+    roof_fit = {"kernel": "gp_fit_predict_kernel<20>", "bound": "fp64", "achieved": fit_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": fit_tf / fp64_peak if fp64_peak else None,
+                "traffic": 772608, "traffic_source": "profiles/r01/fit_r1b.summary.csv (dram read+write bytes per launch)",
+                "peak_source": peak_src,
                 "per_launch": {"launches": fit_n // args.steps, "avg_ms": fit_ms / max(fit_n, 1),
                                "nll_evals": nll_evals / max(fit_n, 1), "flops_per_eval": nll_flops(m)},
-                "share_of_step": fit_ms / (ms_step * args.steps)}
-    # the fine propagator launch (first rk launch of each step carries all slices)
+                "share_of_step": fit_ms / (ms_step * args.steps),
+                "note": "latency-bound: 14% of the searches run to SciPy's maxfev=400, a launch lasts as long as its "
+                        "longest serial chain of evaluations (DESIGN.md 4.5)"}
+    fine_ms = sum(a.elapsed_time(b) for a, b in fine_events) / max(len(fine_events), 1)
     f_flops = rk_flops(d, 11) * args.fine_steps * math.ceil(N / world)
+    rk_tf = f_flops / (fine_ms * 1e-3) / 1e12 if fine_ms > 0 else 0.0
+    roof_rk = {"kernel": "rk_fhn_tile_kernel<11,64>", "bound": "fp64", "achieved": rk_tf, "peak": fp64_peak,
+               "unit": "TFLOP/s", "frac": rk_tf / fp64_peak if fp64_peak else None,
+               "traffic": 2124544, "traffic_source": "profiles/r01/rk_r1d.summary.csv (dram read+write bytes per launch)",
+               "peak_source": peak_src,
+               "per_launch": {"launches": 1, "avg_ms": fine_ms, "slices": math.ceil(N / world),
+                              "steps_per_slice": args.fine_steps, "flops_per_slice_step": rk_flops(d, 11)},
+               "share_of_step": fine_ms / ms_step}
+    roofline, other = (roof_rk, roof_fit) if roof_rk["share_of_step"] >= roof_fit["share_of_step"] else (roof_fit, roof_rk)
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] // args.steps} for k, v in prof.items()}
 
     sweep_ms = sum(prof[k][0] for k in ("knn", "gp_prep", "gp_fit")) / args.steps
     line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "clocks": clk, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+            "clocks": clk, "gpu_launches": int(launches), "roofline": roofline, "roofline_second_kernel": other,
+            "kernels": kernels,
             "fits_per_s": (N - 1) * d / (ms_step * 1e-3), "nm_runs_per_s": nm_runs / args.steps / (ms_step * 1e-3),
             "nll_evals_per_s": nll_evals / args.steps / (ms_step * 1e-3),
             "nll_evals_per_nm_run": nll_evals / max(nm_runs, 1),
@@ -278,7 +298,7 @@ def main():
         line["e2e"] = run_e2e(args, nn, ode, solver, cfg, h, dev, world, rank, sync_all, dist)
     # ---- CPU baseline: the oracle port on this host's cores (rank 0, N=1 only) --------------------
     if world == 1 and not args.no_cpu_baseline:
-        samples, cores, n_dims = cpu_sample(args, n_dims_per_core=8, n_steps=1, warm=0)
+        samples, cores, n_dims = cpu_sample(args, n_dims_per_core=1 << 20, n_steps=1, warm=0)
         r = samples[0]
         line["cpu_baseline"] = {
             "value": 1.0 / r["t_iter"], "unit": "iters/s", "cores": cores, "kind": "port",

@@ -63,8 +63,10 @@ static int ensure_done_zero(nngp_handle_t h, void* ws_fit, int nq, int d, int m,
 }
 
 void* nngp_workspace(nngp_handle_t h, size_t bytes) {
-  if (bytes <= h->ws_bytes) return h->ws;
+  // whoever asks for the block may overwrite the (left-zero) completion counters of an earlier fit:
+  // the next fit clears them again (ensure_done_zero)
   h->done_ptr = nullptr;
+  if (bytes <= h->ws_bytes) return h->ws;
   // grow: work already enqueued may still use the old block
   cudaDeviceSynchronize();
   if (h->ws) cudaFree(h->ws);

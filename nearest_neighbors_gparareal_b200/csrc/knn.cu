@@ -151,6 +151,47 @@ sqdist_kernel(const double* __restrict__ XT, long long cap, long long n, int d,
     if (q0 + t < nq) dist[(long long)(q0 + t) * n + i] = acc[t];
 }
 
+// One query (the sweep's case: Q = 1, n <= a few thousand rows, so only ~100 warps exist and the scan is
+// latency-bound): the strict left-to-right sum is a serial chain of d additions per row, so the loads
+// must run ahead of it -- PF coordinates of the row are fetched in one batch (independent loads, L2
+// hits) while the previous batch is being accumulated.
+template <int PF>
+__global__ void __launch_bounds__(128)
+sqdist_one_kernel(const double* __restrict__ XT, long long cap, long long n, int d,
+                  const double* __restrict__ Q, double* __restrict__ dist) {
+  extern __shared__ double qs[];  // [d]
+  const double* q = Q + (long long)blockIdx.y * d;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) qs[e] = q[e];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* xp = XT + i;
+  double acc = 0.0;
+  double cur[PF], nxt[PF];
+  const int nb = d / PF;
+#pragma unroll
+  for (int u = 0; u < PF; u++) cur[u] = (nb > 0) ? xp[(long long)u * cap] : 0.0;
+  for (int b = 0; b < nb; b++) {
+    const int j0 = b * PF;
+    if (b + 1 < nb) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) nxt[u] = xp[(long long)(j0 + PF + u) * cap];
+    }
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const double diff = qs[j0 + u] - cur[u];
+      acc = acc + diff * diff;
+    }
+#pragma unroll
+    for (int u = 0; u < PF; u++) cur[u] = nxt[u];
+  }
+  for (int j = nb * PF; j < d; j++) {
+    const double diff = qs[j] - xp[(long long)j * cap];
+    acc = acc + diff * diff;
+  }
+  dist[(long long)blockIdx.y * n + i] = acc;
+}
+
 // query coordinates straight from global memory (any d)
 __global__ void __launch_bounds__(128)
 sqdist_kernel_gq(const double* __restrict__ XT, long long cap, long long n, int d,
@@ -268,7 +309,9 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
   } else if (nq >= 4 && 4 * qrow <= lim) {
     sqdist_kernel<4><<<dim3(gx, (nq + 3) / 4), tb, 4 * qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, nq, dist);
   } else if (qrow <= lim) {
-    sqdist_kernel<1><<<dim3(gx, nq), tb, qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, nq, dist);
+    // few queries: 64 rows per CTA spread the (few) warps over more SMs
+    const unsigned g1 = (unsigned)((n + 63) / 64);
+    sqdist_one_kernel<16><<<dim3(g1, nq), 64, qrow, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, dist);
   } else {
     sqdist_kernel_gq<<<dim3(gx, nq), tb, 0, st>>>(h->ds_xt, h->ds_cap, n, d, d_q, dist);
   }

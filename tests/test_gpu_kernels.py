@@ -362,6 +362,24 @@ def test_fit_predict_vs_oracle(handle, n, d, m, R):
     assert np.all(det['fval_opt'][0] <= odet['fval_opt'] + 0.2 * np.abs(odet['fval_opt']))
 
 
+def test_predict_is_repeatable_after_other_workspace_users(handle):
+    """the fit kernel leaves its completion counters zero for the next launch; anything else that uses the
+    handle's workspace in between (micro-benchmarks, a large kNN) must not leave them dirty"""
+    rng = np.random.default_rng(3)
+    n, d, m = 900, 64, 20
+    x, y = make_dataset(rng, n, d)
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    q = x[5:6] + 1e-3
+    starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+    first = handle.predict_host(q, m, starts, 1, 0.1, 0.1)["pred"]
+    handle.bench_fp64(200)
+    handle.knn_host(x[:64] + 1e-3, m)
+    again = handle.predict_host(q, m, starts, 1, 0.1, 0.1)["pred"]
+    assert np.all(np.isfinite(first)) and np.array_equal(first, again)
+
+
 @pytest.mark.parametrize("name", ["lorenz_N50_m11", "hopf_N32_m15", "burgers_d32_N32_m12", "fhn_d32_N32_m12"])
 def test_predict_on_reference_run_samples(handle, name):
     """device predict on (query, dataset prefix, starts) recorded inside a run of the unmodified
