@@ -744,7 +744,11 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
     case NNGP_SYS_THOMAS: SMALL(NNGP_SYS_THOMAS); break;
     case NNGP_SYS_FHN_PDE: {
       const int dx = (int)A.p[0];
-      if (!A.normalize && (dx & 1) == 0 && dx >= 4 && getenv("NNGP_RK_NO_TILE") == nullptr) {
+      // the 2x2-tile kernel is faster at every slice count (measured 64..592 slices per GPU,
+      // profiles/r01/rk_sweep.log); NNGP_RK_TILE=0 forces the one-point-per-thread kernel (tests).
+      // Tried and rejected (slower): two slices per 128-thread CTA, left/right neighbours by shuffle.
+      const char* force = getenv("NNGP_RK_TILE");
+      if (!A.normalize && (dx & 1) == 0 && dx >= 4 && !(force && force[0] == '0')) {
         if (npts / 4 <= 64)
           launch_fhn_tile<64>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
         else

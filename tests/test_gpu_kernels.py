@@ -103,7 +103,7 @@ def test_rk_many_slices_both_step_conventions_vs_oracle():
 @pytest.mark.parametrize("d_x", [4, 6, 16, 18])
 def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
     """the 2x2-points-per-thread FHN kernel (csrc/rk.cu rk_fhn_tile_kernel) returns the bits of the
-    one-point-per-thread kernel (NNGP_RK_NO_TILE selects the latter), all RK methods, and both agree with
+    one-point-per-thread kernel (NNGP_RK_TILE=1 / 0 force one or the other), all RK methods, and both agree with
     the NumPy oracle to 1e-12 scaled"""
     import os
     rng = np.random.default_rng(d_x)
@@ -114,12 +114,13 @@ def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
     t1 = t0 + 0.7
     for F, steps in (('RK8', 23), ('RK4', 11), ('RK2', 6), ('RK1', 5)):
         s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=steps, F=F, G='RK4')
-        got = s.run_F_batch(t0, t1, u0)
-        os.environ["NNGP_RK_NO_TILE"] = "1"
         try:
+            os.environ["NNGP_RK_TILE"] = "1"
+            got = s.run_F_batch(t0, t1, u0)
+            os.environ["NNGP_RK_TILE"] = "0"
             ref = s.run_F_batch(t0, t1, u0)
         finally:
-            del os.environ["NNGP_RK_NO_TILE"]
+            del os.environ["NNGP_RK_TILE"]
         assert np.array_equal(got, ref), F
         want = np.stack([ork.rk_last(o.f, F, t0[i], t1[i], steps, u0[i]) for i in range(n)])
         assert scaled_err(got, want) < 1e-12, F
