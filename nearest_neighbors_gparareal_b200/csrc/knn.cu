@@ -224,31 +224,36 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
 
+// Top-m of the keys (dist[i], id(i)), i in this CTA's chunk of [0, n): id(i) = in_idx[i] when in_idx is
+// given (second level: merging the per-chunk candidates), else i.  Grid (chunks, queries); each CTA writes
+// m sorted (distance, index) pairs, padded with (+inf, INT64_MAX) when the chunk holds fewer.
 __global__ void __launch_bounds__(KNN_SEL_THREADS)
-select_kernel(const double* __restrict__ dist, long long n, int m, long long* __restrict__ idx_out,
-              double* __restrict__ dist_out) {
+select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_idx, long long n,
+              long long chunk, int m, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
   constexpr int NW = KNN_SEL_THREADS / 32;
   __shared__ double cd[NW * 32];
   __shared__ long long ci[NW * 32];
-  const int q = blockIdx.x;
+  const int q = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const double* dq = dist + (long long)q * n;
+  const long long* iq = in_idx ? in_idx + (long long)q * n : nullptr;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(n, lo + chunk);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const long long IMAX = 0x7fffffffffffffffLL;
   // lane l holds the l-th smallest key seen by this warp (l < m)
   double bd = INF;
   long long bi = IMAX;
-  for (long long base = (long long)w * 32; base < n; base += KNN_SEL_THREADS) {
+  for (long long base = lo + (long long)w * 32; base < hi; base += KNN_SEL_THREADS) {
     const long long i = base + lane;
     double c = INF;
     long long cidx = IMAX;
-    if (i < n) {
+    if (i < hi) {
       c = dq[i];
-      cidx = i;
+      cidx = iq ? iq[i] : i;
     }
     const double td = shfl_d(bd, m - 1);
     const long long ti = shfl_ll(bi, m - 1);
-    unsigned pending = __ballot_sync(0xffffffffu, (i < n) && key_less(c, cidx, td, ti));
+    unsigned pending = __ballot_sync(0xffffffffu, (cidx != IMAX) && key_less(c, cidx, td, ti));
     while (pending) {
       const int src = __ffs(pending) - 1;
       pending &= pending - 1;
@@ -273,21 +278,46 @@ select_kernel(const double* __restrict__ dist, long long n, int m, long long* __
   ci[w * 32 + lane] = (lane < m) ? bi : IMAX;
   __syncthreads();
   // merge by ranking: all real keys are distinct (unique index), so ranks are unique
+  const long long ob = ((long long)q * gridDim.x + blockIdx.x) * m;
   const double md = cd[threadIdx.x];
   const long long mi = ci[threadIdx.x];
+  int nreal = 0;
+  for (int t = 0; t < NW * 32; t++) nreal += (ci[t] != IMAX) ? 1 : 0;
   if (mi != IMAX) {
     int rank = 0;
     for (int t = 0; t < NW * 32; t++) rank += key_less(cd[t], ci[t], md, mi) ? 1 : 0;
     if (rank < m) {
-      idx_out[(long long)q * m + rank] = mi;
-      dist_out[(long long)q * m + rank] = md;
+      idx_out[ob + rank] = mi;
+      dist_out[ob + rank] = md;
     }
+  }
+  if ((int)threadIdx.x < m && (int)threadIdx.x >= nreal) {  // chunk with fewer than m rows: padding
+    idx_out[ob + threadIdx.x] = IMAX;
+    dist_out[ob + threadIdx.x] = INF;
   }
 }
 
+static constexpr long long KNN_CHUNK = 4096;  // least rows per first-level selection CTA
+
+// Rows per first-level CTA: the scan of one query is split only as far as it takes to fill the GPU
+// (about two CTAs per SM over all queries) -- every CTA pays the fill of its own top-m lists, so
+// with many queries one CTA per query is the faster arrangement.
+static long long knn_chunk_rows(int nq, long long n) {
+  const long long want = (296 + nq - 1) / nq;  // CTAs per query
+  long long chunk = (n + want - 1) / want;
+  if (chunk < KNN_CHUNK) chunk = KNN_CHUNK;
+  return chunk;
+}
+
+static inline size_t knn_pad256(size_t b) { return ((b + 255) / 256) * 256; }
+
+// [distances nq*n | per-chunk candidate distances nq*chunks*m | candidate indices]
 size_t knn_workspace_bytes(int nq, long long n, int m) {
-  (void)m;
-  return sizeof(double) * (size_t)nq * (size_t)n;
+  const long long cr = knn_chunk_rows(nq, n);
+  const size_t chunks = (size_t)((n + cr - 1) / cr);
+  size_t b = knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
+  if (chunks > 1) b += 2 * knn_pad256(sizeof(double) * (size_t)nq * chunks * (size_t)m);
+  return b;
 }
 
 int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
@@ -317,8 +347,21 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
   }
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
-  select_kernel<<<nq, KNN_SEL_THREADS, 0, st>>>(dist, n, m, d_idx, d_dist);
-  h->launches++;
+  const long long chunk_rows = knn_chunk_rows(nq, n);
+  const long long chunks = (n + chunk_rows - 1) / chunk_rows;
+  if (chunks == 1) {
+    select_kernel<<<dim3(1, nq), KNN_SEL_THREADS, 0, st>>>(dist, nullptr, n, n, m, d_idx, d_dist);
+    h->launches++;
+  } else {
+    // two levels: top-m of every 4096-row chunk in parallel, then top-m of the chunks' candidates
+    char* base = (char*)ws + knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
+    double* cand_d = (double*)base;
+    long long* cand_i = (long long*)(base + knn_pad256(sizeof(double) * (size_t)nq * chunks * m));
+    select_kernel<<<dim3((unsigned)chunks, nq), KNN_SEL_THREADS, 0, st>>>(dist, nullptr, n, chunk_rows, m, cand_i, cand_d);
+    const long long nc = chunks * m;
+    select_kernel<<<dim3(1, nq), KNN_SEL_THREADS, 0, st>>>(cand_d, cand_i, nc, nc, m, d_idx, d_dist);
+    h->launches += 2;
+  }
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
 }

@@ -196,7 +196,7 @@ def make_dataset(rng, n, d):
 
 @pytest.mark.parametrize("n,d,m,nq", [(40, 3, 11, 1), (300, 3, 11, 5), (2000, 32, 12, 9), (3055, 512, 20, 1),
                                        (3055, 512, 20, 12), (5000, 128, 30, 33), (65, 7, 32, 3), (20, 2, 20, 2),
-                                       (700, 1100, 5, 6)])
+                                       (700, 1100, 5, 6), (20000, 8, 32, 2), (8193, 3, 20, 40), (4097, 5, 17, 1)])
 def test_knn_bit_exact(handle, n, d, m, nq):
     """index sets AND squared distances bit-identical to argsort(cdist(q, x, 'sqeuclidean'))[:m]"""
     rng = np.random.default_rng(n + d)
@@ -230,6 +230,18 @@ def test_knn_ties_broken_by_index_and_edge_cases(handle):
     oi, od = onn.knn(q, x, 9)
     assert np.array_equal(idx[0], oi) and np.array_equal(dist[0], od)
     assert list(idx[0][:3]) == [3, 33, 63]  # same distance, ascending index
+    # exact ties across the 4096-row chunks of the two-level selection: still ascending index
+    big = np.tile(base, (300, 1))  # 9000 rows, every row repeated 300 times
+    handle.dataset_reset()
+    handle.dataset_reserve(9000, 4)
+    handle.dataset_append_host(big, np.zeros_like(big))
+    idx, dist = handle.knn_host(q[None], 25)
+    oi, od = onn.knn(q, big, 25)
+    assert np.array_equal(idx[0], oi) and np.array_equal(dist[0], od)
+    assert list(idx[0][:4]) == [3, 33, 63, 93] and idx[0].max() > 4096 * 0  # same distance, ascending index
+    handle.dataset_reset()
+    handle.dataset_reserve(200, 4)
+    handle.dataset_append_host(x, y)
     # query equal to a dataset row: distance exactly 0 first
     idx, dist = handle.knn_host(base[5][None], 3)
     assert dist[0, 0] == 0.0 and idx[0, 0] == 5
