@@ -87,3 +87,31 @@ def test_plain_parareal_matches_published_K():
     assert out['k'] == 15 and out['conv_int'] == [1, 2, 3, 5, 8, 14, 17, 20, 26, 30, 33, 37, 40, 43, 50]
     out2 = nn.Parareal(ode, solver, verbose='', **cfg).run(model='parareal', pool=nn.CudaPool(), parall='mpi')
     assert out2['k'] == 15 and np.array_equal(out2['u_last'], out['u'])
+
+
+def test_full_size_fhn_target_against_published_run():
+    """BASELINE.json configs[3] at its full, published size: FHN-PDE d=512, N=512 slices, m=20, RK8 with 195 325
+    steps per slice (FHN_PDE.py:46-57,174-175), device-resident driver.  Checked against the reference's
+    published pickle FHN_scal_times_16_512_nngp (tests/golden/published.json): the per-iteration error maxima
+    of the first three iterations agree to 1e-4 relative (they are governed by F and G, which are exact),
+    the first converged counts are equal, and K is the published 6 or one less (K is +-1 sensitive to
+    last-bit ties in the reference itself).  Size-independent properties: converged,
+    errors decrease, every slice finite, dataset rows = sum over iterations of (N - I + 1)."""
+    import json
+    import os
+    ode = nn.FHN_PDE(d_x=16)
+    cfg = nn.Config(ode, d_x=16).get()
+    cfg["Nf"] = 195325
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+    par = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=5e-7, verbose="")
+    out = par.run(model="nngp", nn=20, seed=45)
+    pub = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "published.json")))
+    ref = pub["FHN_scal_times/FHN_scal_times_16_512_nngp"]["NNGP"]
+    assert out["converged"] and np.all(np.isfinite(out["u"]))
+    assert out["k"] in (ref["K"], ref["K"] - 1), out["conv_int"]
+    assert out["conv_int"][:4] == ref["conv_int"][:4] and out["conv_int"][-1] == 512
+    errs = np.nanmax(out["err"], axis=0)
+    np.testing.assert_allclose(errs[:3], ref["err_max_per_iter"][:3], rtol=1e-4)
+    assert np.all(np.diff(errs) < 0)
+    I_before = [0] + out["conv_int"][:-1]
+    assert out["n_rows"] == sum(512 - (I + 1) + 1 for I in I_before)
