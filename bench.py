@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--fine-steps", type=int, default=195325,
                     help="RK8 steps per slice; 195325 = the published run (FHN_PDE.py:53-54), 25 = configs.py preset")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicated-sweep", action="store_true",
+                    help="N>1: every rank runs the whole sweep (north_star's layout) instead of sharding the fits by dimension")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-class event timings here (json)")
@@ -193,7 +195,8 @@ def main():
     cfg["tspan"] = [0, cfg["tspan"][1] * N / 512]
     cfg["Nf"] = args.fine_steps
     solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
-    par = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=N, epsilon=5e-7, verbose="")
+    par = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=N, epsilon=5e-7, verbose="",
+                            shard_sweep=not args.replicated_sweep)
     model = nn.CudaNNGP(n=d, N=N, nn=m, seed=45, handle=h)
     st = par.device_setup(model)
     torch.cuda.synchronize(dev)

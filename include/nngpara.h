@@ -136,6 +136,14 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
                const double* d_t, int N, int I, int m, int n_restarts,
                const signed char* d_starts, double fatol, double xatol, double* d_u_next,
                double* d_uG_next, int d, void* stream);
+/* One rank's share of the same sweep (optional sharding of the d*9*R fits of a predict by
+ * output dimension): slices i_first .. i_first+i_count-1 of the sweep that starts at slice I; G and kNN in full,
+ * fits and u_next[i+1] only for dimensions [j0, j0+dl).  The caller all-gathers row i+1 of u_next over the ranks
+ * (d/W doubles each) before the next slice; results are bit-identical to nngp_sweep.                          */
+int nngp_sweep_shard(nngp_handle_t h, int sys, int method_g, int h_mode, long long steps_g,
+                     const double* d_t, int N, int I, int i_first, int i_count, int m, int n_restarts,
+                     const signed char* d_starts, double fatol, double xatol, double* d_u_next,
+                     double* d_uG_next, int d, int j0, int dl, void* stream);
 /* parareal.py:336-339: x <- u_cur[I-1:N], D <- uF[I:N+1] - uG_cur[I:N+1] appended on device. */
 int nngp_append_iteration(nngp_handle_t h, const double* d_u_cur, const double* d_uF,
                           const double* d_uG_cur, int N, int I, int d, void* stream);

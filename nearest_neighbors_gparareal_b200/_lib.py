@@ -48,6 +48,7 @@ SIGNATURES = {
     "nngp_gp_nll": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp]),
     "nngp_gp_mean": (ci, [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]),
     "nngp_sweep": (ci, [vp, ci, ci, ci, cll, vp, ci, ci, ci, ci, vp, cd, cd, vp, vp, ci, vp]),
+    "nngp_sweep_shard": (ci, [vp, ci, ci, ci, cll, vp, ci, ci, ci, ci, ci, ci, vp, cd, cd, vp, vp, ci, ci, ci, vp]),
     "nngp_append_iteration": (ci, [vp, vp, vp, vp, ci, ci, ci, vp]),
     "nngp_rowwise_maxabs_diff": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "nngp_selftest_math": (ci, [vp, vp, ci, vp, vp, vp, vp]),
@@ -246,6 +247,13 @@ class Handle:
         self.check(self.lib.nngp_sweep(self.h, sys, method_g, h_mode, int(steps_g), _ptr(d_t), int(N), int(I),
                                        int(m), int(n_restarts), _ptr(d_starts), float(fatol), float(xatol),
                                        _ptr(d_u_next), _ptr(d_uG_next), int(d), stream))
+
+    def sweep_shard(self, sys, method_g, h_mode, steps_g, d_t, N, I, i_first, i_count, m, n_restarts, d_starts, fatol,
+                    xatol, d_u_next, d_uG_next, d, j0, dl, stream=None):
+        self.check(self.lib.nngp_sweep_shard(self.h, sys, method_g, h_mode, int(steps_g), _ptr(d_t), int(N), int(I),
+                                             int(i_first), int(i_count), int(m), int(n_restarts), _ptr(d_starts),
+                                             float(fatol), float(xatol), _ptr(d_u_next), _ptr(d_uG_next), int(d),
+                                             int(j0), int(dl), stream))
 
     def append_iteration(self, d_u_cur, d_uF, d_uG_cur, N, I, d, stream=None):
         self.check(self.lib.nngp_append_iteration(self.h, _ptr(d_u_cur), _ptr(d_uF), _ptr(d_uG_cur), int(N),

@@ -582,6 +582,54 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
   return 0;
 }
 
+// One rank's share of the sweep for slices i_first .. i_first+i_count-1 (I = first slice of the whole
+// sweep: d_starts holds the starts of predicts I, I+1, ... in order): G and the neighbour search are done
+// in full (replicated, cheap), the d*9*R searches only for the output dimensions [j0, j0+dl); u_next[i+1]
+// is written for those dimensions only -- the caller all-gathers the row before the next slice.
+int nngp_sweep_shard(nngp_handle_t h, int sys, int method_g, int h_mode, long long steps_g,
+                     const double* d_t, int N, int I, int i_first, int i_count, int m, int n_restarts,
+                     const signed char* d_starts, double fatol, double xatol, double* d_u_next,
+                     double* d_uG_next, int d, int j0, int dl, void* stream) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  if (d != s->d || d != h->ds_d) return nngp_fail(h, "sweep: d=%d, system d=%d, dataset d=%d", d, s->d, h->ds_d);
+  if (I < 0 || I > N || i_first < I || i_count < 0 || i_first + i_count > N)
+    return nngp_fail(h, "sweep_shard: slices [%d,%d) outside [%d,%d)", i_first, i_first + i_count, I, N);
+  if (j0 < 0 || dl < 1 || j0 + dl > d) return nngp_fail(h, "sweep_shard: dimensions [%d,%d) outside [0,%d)", j0, j0 + dl, d);
+  if (n_restarts < 1) return nngp_fail(h, "sweep: n_restarts=%d < 1", n_restarts);
+  cudaStream_t st = as_stream(stream);
+  const long long n = h->ds_rows;
+  const size_t bk = Carver::pad(knn_workspace_bytes(1, n, m));
+  const size_t bf = Carver::pad(gp_fit_ws_bytes(1, d, m, n_restarts));
+  const size_t bi = Carver::pad(sizeof(long long) * m), bd = Carver::pad(sizeof(double) * m);
+  const int nruns = NNGP_N_JITTER * n_restarts;
+  const int seg_len = dl * nruns;
+  const size_t bo = Carver::pad(sizeof(int) * (size_t)seg_len);
+  char* ws = (char*)nngp_workspace(h, bk + bf + bi + bd + bo);
+  if (!ws) return nngp_fail(h, "sweep: out of device memory");
+  void* kws = ws;
+  void* fws = ws + bk;
+  long long* idx = (long long*)(ws + bk + bf);
+  double* dist = (double*)(ws + bk + bf + bi);
+  int* order = (int*)(ws + bk + bf + bi + bd);
+  if (int rc = ensure_done_zero(h, fws, 1, d, m, n_restarts, st)) return rc;
+  const size_t per_predict = (size_t)d * nruns * 2;
+  for (int i = i_first; i < i_first + i_count; i++) {
+    double* ui = d_u_next + (long long)i * d;
+    double* un = d_u_next + (long long)(i + 1) * d;
+    double* gn = d_uG_next + (long long)(i + 1) * d;
+    const signed char* starts_i = d_starts + (size_t)(i - I) * per_predict;
+    if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
+    if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
+    if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
+    if (int rc = gp_order_launch(h, starts_i + (size_t)j0 * nruns * 2, 1, seg_len, 0, order, st)) return rc;
+    if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), order, 1, m, n_restarts, starts_i, fatol,
+                                       xatol, un, gn, d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, j0, dl))
+      return rc;
+  }
+  return 0;
+}
+
 int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rcp,
                        double* d_exp10, void* stream) {
   return selftest_math_launch(h, d_x, n, d_exp_neg, d_rcp, d_exp10, as_stream(stream));

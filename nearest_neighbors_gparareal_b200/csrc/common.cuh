@@ -123,7 +123,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
                           double fatol, double xatol, double* d_pred, const double* d_add,
                           long long ld_pred, double* d_theta_opt, double* d_jitter_opt,
                           double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
-                          cudaStream_t st);
+                          cudaStream_t st, int j0 = 0, int dl = -1);
 int gp_nll_launch(nngp_handle_t h, const long long* d_idx, const double* d_r2, int nq, int m,
                   int nt, const double* d_theta, const double* d_jitter10, double* d_nll,
                   cudaStream_t st);

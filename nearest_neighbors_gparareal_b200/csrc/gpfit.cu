@@ -637,6 +637,7 @@ struct FitArgs {
   unsigned int* queue;    // next task to hand out; zero on entry
   const int* order;       // optional [ntasks]: queue position -> task (longest searches first)
   int d, m, R, ntasks;
+  int j0, dl;             // output dimensions [j0, j0+dl) handled by this launch (a rank's share; dl = d: all)
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
 };
@@ -676,8 +677,11 @@ gp_fit_predict_kernel(FitArgs A) {
     }
     task = __shfl_sync(FULL, task, 0);
     if (task >= A.ntasks) break;
+    // task and qj number the searches / (query, dim) pairs of THIS launch; gtask, gqj are their positions
+    // in the full [nq, d, 9, R] arrays (identical when the launch covers every dimension)
     const int qj = task / nruns, run = task - qj * nruns;
-    const int q = qj / d, j = qj - q * d;
+    const int q = qj / A.dl, j = A.j0 + (qj - q * A.dl);
+    const long long gqj = (long long)q * d + j, gtask = gqj * nruns + run;
     const int a = run / R;
     const double* r2 = A.r2 + (long long)q * m * m;
     if (q != q_loaded) {
@@ -685,7 +689,7 @@ gp_fit_predict_kernel(FitArgs A) {
       q_loaded = q;
     }
     const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
-    const signed char* st = A.starts + (long long)task * 2;
+    const signed char* st = A.starts + gtask * 2;
     const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol, P, y, m,
                                    lane, Lt, hml);
     unsigned int prior = 0;
@@ -695,11 +699,11 @@ gp_fit_predict_kernel(FitArgs A) {
       A.res[(long long)task * 3 + 2] = o.x1;
       atomicAdd(A.counters, 1ULL);
       atomicAdd(A.counters + 1, (unsigned long long)o.nfev);
-      if (A.nfev) A.nfev[task] = o.nfev;
-      if (A.fvals) A.fvals[task] = o.f;
+      if (A.nfev) A.nfev[gtask] = o.nfev;
+      if (A.fvals) A.fvals[gtask] = o.f;
       if (A.thetas) {
-        A.thetas[(long long)task * 2] = o.x0;
-        A.thetas[(long long)task * 2 + 1] = o.x1;
+        A.thetas[gtask * 2] = o.x0;
+        A.thetas[gtask * 2 + 1] = o.x1;
       }
       __threadfence();
       prior = atomicAdd(A.done + qj, 1u);
@@ -739,11 +743,11 @@ gp_fit_predict_kernel(FitArgs A) {
       if (A.add) mean = mean + A.add[op];
       A.pred[op] = mean;
       if (A.theta_opt) {
-        A.theta_opt[(long long)qj * 2] = th0;
-        A.theta_opt[(long long)qj * 2 + 1] = th1;
+        A.theta_opt[gqj * 2] = th0;
+        A.theta_opt[gqj * 2 + 1] = th1;
       }
-      if (A.jitter_opt) A.jitter_opt[qj] = (double)(ab - 20);
-      if (A.fval_opt) A.fval_opt[qj] = fb;
+      if (A.jitter_opt) A.jitter_opt[gqj] = (double)(ab - 20);
+      if (A.fval_opt) A.fval_opt[gqj] = fb;
     }
   }
 }
@@ -961,12 +965,14 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
                           double fatol, double xatol, double* d_pred, const double* d_add,
                           long long ld_pred, double* d_theta_opt, double* d_jitter_opt,
                           double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
-                          cudaStream_t st) {
+                          cudaStream_t st, int j0, int dl) {
   if (nq <= 0) return 0;
   if (m < 1 || m > NNGP_MAX_NEIGHBOURS) return nngp_fail(h, "fit: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS);
   if (R < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", R);
   const int d = h->ds_d;
-  const long long ntasks = (long long)nq * d * NNGP_N_JITTER * R;
+  if (dl < 0) dl = d;
+  if (j0 < 0 || dl < 1 || j0 + dl > d) return nngp_fail(h, "fit: dimension block [%d,%d) outside [0,%d)", j0, j0 + dl, d);
+  const long long ntasks = (long long)nq * dl * NNGP_N_JITTER * R;
   if (ntasks > 0x7fffffffLL) return nngp_fail(h, "fit: %lld searches in one launch (limit 2^31)", ntasks);
   char* base = (char*)ws;
   FitArgs A;
@@ -978,7 +984,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.order = order;
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
-  A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
+  A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
   int rc = 0;
   DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   return rc;

@@ -30,6 +30,13 @@ def slice_block(I, N, rank, world):
     return chunk, lo, cnt
 
 
+def dim_block(d, rank, world):
+    """Output dimensions [j0, j0+dl) whose fits `rank` runs when the sweep is sharded by dimension
+    (equal blocks: d must be a multiple of world)."""
+    dl = d // world
+    return rank * dl, dl
+
+
 def gather_fine_rows(uF, I, chunk, rank, world, group=None):
     """The one collective of an iteration: every rank wrote rows uF[lo+1 : lo+1+cnt] of its block;
     afterwards all ranks hold uF[I+1 : N+1].  uF needs world*chunk rows after row I."""
@@ -226,11 +233,15 @@ class PararealDevice(Parareal):
     """
     keep_history = False
 
-    def __init__(self, ode, solver, tspan, N, epsilon=5e-7, verbose='v', group=None, **kwargs):
+    def __init__(self, ode, solver, tspan, N, epsilon=5e-7, verbose='v', group=None, shard_sweep=True, **kwargs):
         super().__init__(ode, solver, tspan, N, epsilon=epsilon, verbose=verbose, **kwargs)
         if not isinstance(solver, CudaSolverRK):
             raise Exception('PararealDevice needs a CudaSolverRK')
         self.group = group
+        # W > 1 ranks: split the d*9*R fits of every predict by output dimension over the ranks and
+        # all-gather the d/W predictions per slice ("optional -- measure first":
+        # measured in profiles/); needs d % W == 0, otherwise the sweep is replicated
+        self.shard_sweep = shard_sweep
         self.events = []
 
     def _world(self):
@@ -324,8 +335,19 @@ class PararealDevice(Parareal):
             if starts is None:
                 starts = torch.from_numpy(model.draw_starts(N - I)).to(st['dev'])
             st['starts'] = starts  # keep alive until the stream has consumed it
-            h.sweep(st['sys'], st['mG'], solver.h_mode, solver.Ng, st['t'], N, I, m, model.n_restarts, starts,
-                    model.fatol, model.xatol, st['u_next'], st['uG_next'], n, st['stream'])
+            world = st['world']
+            if world > 1 and self.shard_sweep and n % world == 0:
+                import torch.distributed as dist
+                j0, dl = dim_block(n, st['rank'], world)
+                for i in range(I, N):
+                    h.sweep_shard(st['sys'], st['mG'], solver.h_mode, solver.Ng, st['t'], N, I, i, 1, m,
+                                  model.n_restarts, starts, model.fatol, model.xatol, st['u_next'], st['uG_next'],
+                                  n, j0, dl, st['stream'])
+                    row = st['u_next'][i + 1]
+                    dist.all_gather_into_tensor(row, row[j0:j0 + dl], group=self.group)
+            else:
+                h.sweep(st['sys'], st['mG'], solver.h_mode, solver.Ng, st['t'], N, I, m, model.n_restarts, starts,
+                        model.fatol, model.xatol, st['u_next'], st['uG_next'], n, st['stream'])
             model.train_count += (N - I) * n * N_JITTER * model.n_restarts
         else:
             for i in range(I, N):

@@ -115,3 +115,33 @@ def test_full_size_fhn_target_against_published_run():
     assert np.all(np.diff(errs) < 0)
     I_before = [0] + out["conv_int"][:-1]
     assert out["n_rows"] == sum(512 - (I + 1) + 1 for I in I_before)
+
+
+def test_dimension_sharded_sweep_equals_replicated_sweep_bitwise():
+    """nngp_sweep_shard (one rank's share of the fits of every predict, by output dimension) emulated on one
+    GPU: running the W blocks one after the other for every slice fills u_next exactly as nngp_sweep does"""
+    import torch
+    from nearest_neighbors_gparareal_b200 import _lib
+    z, cfg, mkw, p = build("fhn_d32_N32_m12", nn.PararealDevice)
+    model = nn.CudaNNGP(n=p.n, N=p.N, **mkw)
+    st = p.device_setup(model)
+    p.device_fine_step(st)
+    h, I, N, n = st['h'], st['I'], p.N, p.n
+    h.append_iteration(st['u_cur'], st['uF'], st['uG_cur'], N, I, n, st['stream'])
+    m = 12
+    starts = torch.from_numpy(model.draw_starts(N - I)).to(st['dev'])
+    ref_u, ref_g = st['u_next'].clone(), st['uG_next'].clone()
+    h.sweep(st['sys'], st['mG'], p.solver.h_mode, p.solver.Ng, st['t'], N, I, m, 1, starts, 0.1, 0.1, ref_u, ref_g, n,
+            st['stream'])
+    for world in (2, 4):
+        u, g = st['u_next'].clone(), st['uG_next'].clone()
+        for i in range(I, N):
+            for rank in range(world):
+                j0, dl = nn.parareal.dim_block(n, rank, world)
+                h.sweep_shard(st['sys'], st['mG'], p.solver.h_mode, p.solver.Ng, st['t'], N, I, i, 1, m, 1, starts,
+                              0.1, 0.1, u, g, n, j0, dl, st['stream'])
+        torch.cuda.synchronize()
+        assert torch.equal(u, ref_u) and torch.equal(g, ref_g), world
+    with pytest.raises(_lib.NNGPError, match="outside"):
+        h.sweep_shard(st['sys'], st['mG'], p.solver.h_mode, p.solver.Ng, st['t'], N, I, I, 1, m, 1, starts, 0.1, 0.1,
+                      ref_u, ref_g, n, 24, 16, st['stream'])
