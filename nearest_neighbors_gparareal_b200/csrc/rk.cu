@@ -488,38 +488,48 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------
-// FHN, identity normalisation, even d_x: one thread owns a 2x2 block of grid points (both fields).
+// FHN, identity normalisation, even d_x: one thread owns a TY x 2 block of grid points (both fields).
 // ncu (profiles/r01/rk_r1d.summary.csv) shows rk_pde_kernel bound by the shared-memory pipe
 // (8 neighbour loads + 2 stores per point and stage); with 2x2 blocks half of the neighbours are the
 // thread's own registers and the vertical ones come as aligned 16-byte pairs: 12 instead of 20
 // shared-memory accesses per point pair, and 4x fewer threads per barrier.  Per-point arithmetic and
-// summation order are those of FhnPde::eval_k, so both kernels return identical bits.
+// summation order are those of FhnPde::eval_k, so all kernels return identical bits.
+//   TY = 2 (64 threads per 16x16 slice): least shared-memory traffic -- the throughput shape, used
+//          when every SM holds several slices (one GPU: 512 slices on 148 SMs);
+//   TY = 1 (128 threads per slice): a slice spreads over all four SM sub-partitions, each warp
+//          issuing half the FP64 work -- the latency shape, used when a GPU holds at most two slices
+//          per SM (a rank of a multi-GPU run), where a slice's own step time is what counts.
 // ---------------------------------------------------------------------------------------
-template <int S, int TB>
-__global__ void __launch_bounds__(TB, (TB <= 64) ? 4 : 1)
+template <int TY, int TB>
+struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) : ((TB <= 128) ? 4 : 1); };
+
+template <int S, int TY, int TB>
+__global__ void __launch_bounds__(TB, TileOcc<TY, TB>::value)
 rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__ t0s,
                    const double* __restrict__ t1s, const double* __restrict__ u0, long long ld0,
                    double* __restrict__ u1, long long ld1) {
+  constexpr int NV = 2 * TY;  // points per thread, row-major inside the block
   extern __shared__ double sm[];
   const Tableau& T = c_tab[SlotOf<S>::value];
-  const int dx = (int)A.p[0], npts = dx * dx, hx = dx >> 1, ntile = hx * hx;
+  const int dx = (int)A.p[0], npts = dx * dx, hx = dx >> 1, ntile = hx * (dx / TY);
   const bool active = (int)threadIdx.x < ntile;
   const int tt = active ? threadIdx.x : 0;
-  const int ix0 = 2 * (tt % hx), iy0 = 2 * (tt / hx);
-  const int o00 = iy0 * dx + ix0, o10 = o00 + dx;
-  const int oup = ((iy0 == 0 ? dx : iy0) - 1) * dx + ix0;      // row iy0-1, columns ix0, ix0+1
-  const int odn = ((iy0 + 2 == dx) ? 0 : iy0 + 2) * dx + ix0;  // row iy0+2
+  const int ix0 = 2 * (tt % hx), iy0 = TY * (tt / hx);
+  const int o00 = iy0 * dx + ix0;
+  const int oup = ((iy0 == 0 ? dx : iy0) - 1) * dx + ix0;        // row iy0-1, columns ix0, ix0+1
+  const int odn = ((iy0 + TY == dx) ? 0 : iy0 + TY) * dx + ix0;  // row iy0+TY
   const int xl = (ix0 == 0 ? dx : ix0) - 1, xr = (ix0 + 2 == dx) ? 0 : ix0 + 2;
-  const int ol0 = iy0 * dx + xl, ol1 = ol0 + dx, or0 = iy0 * dx + xr, or1 = or0 + dx;
+  const int ol0 = iy0 * dx + xl, or0 = iy0 * dx + xr;
   const long long s = blockIdx.x;
-  double u[2][4], k[2][4][S];
+  double u[2][NV], k[2][NV][S];
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     const double* src = u0 + s * ld0 + c * npts;
-    u[c][0] = src[o00];
-    u[c][1] = src[o00 + 1];
-    u[c][2] = src[o10];
-    u[c][3] = src[o10 + 1];
+#pragma unroll
+    for (int r = 0; r < TY; r++) {
+      u[c][2 * r] = src[o00 + r * dx];
+      u[c][2 * r + 1] = src[o00 + r * dx + 1];
+    }
   }
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
@@ -530,11 +540,11 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
     for (int i = 0; i < S; i++) {
       double* buf = sm + par * (2 * npts);
       par ^= 1;
-      double w[2][4], sn[2][4];
+      double w[2][NV], sn[2][NV];
 #pragma unroll
       for (int c = 0; c < 2; c++) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NV; q++) {
           double x = u[c][q];
 #pragma unroll
           for (int j = 0; j < i; j++)
@@ -542,8 +552,9 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
           w[c][q] = x;
         }
         if (active) {
-          *reinterpret_cast<double2*>(buf + c * npts + o00) = make_double2(w[c][0], w[c][1]);
-          *reinterpret_cast<double2*>(buf + c * npts + o10) = make_double2(w[c][2], w[c][3]);
+#pragma unroll
+          for (int r = 0; r < TY; r++)
+            *reinterpret_cast<double2*>(buf + c * npts + o00 + r * dx) = make_double2(w[c][2 * r], w[c][2 * r + 1]);
         }
       }
       __syncthreads();
@@ -552,15 +563,18 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
         const double* b = buf + c * npts;
         const double2 up = *reinterpret_cast<const double2*>(b + oup);
         const double2 dn = *reinterpret_cast<const double2*>(b + odn);
-        const double l0 = b[ol0], l1 = b[ol1], r0 = b[or0], r1 = b[or1];
-        // (v[iy-1] + v[ix-1]) + (v[ix+1] + v[iy+1]) as in FhnPde::eval_k
-        sn[c][0] = (up.x + l0) + (w[c][1] + w[c][2]);
-        sn[c][1] = (up.y + w[c][0]) + (r0 + w[c][3]);
-        sn[c][2] = (w[c][0] + l1) + (w[c][3] + dn.x);
-        sn[c][3] = (w[c][1] + w[c][2]) + (r1 + dn.y);
+#pragma unroll
+        for (int r = 0; r < TY; r++) {
+          const double l = b[ol0 + r * dx], rr = b[or0 + r * dx];
+          const double ax = (r == 0) ? up.x : w[c][2 * (r - 1)], ay = (r == 0) ? up.y : w[c][2 * (r - 1) + 1];
+          const double bx = (r == TY - 1) ? dn.x : w[c][2 * (r + 1)], by = (r == TY - 1) ? dn.y : w[c][2 * (r + 1) + 1];
+          // (v[iy-1] + v[ix-1]) + (v[ix+1] + v[iy+1]) as in FhnPde::eval_k
+          sn[c][2 * r] = (ax + l) + (w[c][2 * r + 1] + bx);
+          sn[c][2 * r + 1] = (ay + w[c][2 * r]) + (rr + by);
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
+      for (int q = 0; q < NV; q++) {
         const double v0 = w[0][q], v1 = w[1][q];
         const double e1 = fma(-v0, v0, A.q[0]);
         const double e2 = A.p[5] - v1;
@@ -571,7 +585,7 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
 #pragma unroll
     for (int c = 0; c < 2; c++)
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < NV; q++)
 #pragma unroll
         for (int i = 0; i < S; i++)
           if (b_nonzero<S>(i)) u[c][q] = fma(T.b[i], k[c][q][i], u[c][q]);
@@ -580,25 +594,26 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       double* dst = u1 + s * ld1 + c * npts;
-      dst[o00] = u[c][0];
-      dst[o00 + 1] = u[c][1];
-      dst[o10] = u[c][2];
-      dst[o10 + 1] = u[c][3];
+#pragma unroll
+      for (int r = 0; r < TY; r++) {
+        dst[o00 + r * dx] = u[c][2 * r];
+        dst[o00 + r * dx + 1] = u[c][2 * r + 1];
+      }
     }
   }
 }
 
-template <int TB>
+template <int TY, int TB>
 static void launch_fhn_tile(const SysArgs& A, int npts, int method, int h_mode, long long steps, int n,
                             const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
                             long long ld1, cudaStream_t st) {
-  const int threads = ((npts / 4 + 31) / 32) * 32;
+  const int threads = ((npts / (2 * TY) + 31) / 32) * 32;
   const size_t smem = 2 * sizeof(double) * 2 * npts;
   switch (method) {
-    case 1: rk_fhn_tile_kernel<1, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 2: rk_fhn_tile_kernel<2, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 4: rk_fhn_tile_kernel<4, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    default: rk_fhn_tile_kernel<11, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 1: rk_fhn_tile_kernel<1, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 2: rk_fhn_tile_kernel<2, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 4: rk_fhn_tile_kernel<4, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    default: rk_fhn_tile_kernel<11, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
   }
 }
 
@@ -744,15 +759,26 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
     case NNGP_SYS_THOMAS: SMALL(NNGP_SYS_THOMAS); break;
     case NNGP_SYS_FHN_PDE: {
       const int dx = (int)A.p[0];
-      // the 2x2-tile kernel is faster at every slice count (measured 64..592 slices per GPU,
-      // profiles/r01/rk_sweep.log); NNGP_RK_TILE=0 forces the one-point-per-thread kernel (tests).
+      // NNGP_RK_TILE = 0 / 1 / 2 forces the one-point-per-thread kernel / the 2x2 blocks / the 1x2 blocks
+      // (tests, experiments); default 2x2: fastest from 256 slices per GPU up and within 3 % of the 1x2
+      // blocks below (a lone slice is bound by the per-stage latency chain, ~270 cycles, in every shape;
+      // slice-count sweep in profiles/r01/rk_sweep.log).
       // Tried and rejected (slower): two slices per 128-thread CTA, left/right neighbours by shuffle.
       const char* force = getenv("NNGP_RK_TILE");
-      if (!A.normalize && (dx & 1) == 0 && dx >= 4 && !(force && force[0] == '0')) {
-        if (npts / 4 <= 64)
-          launch_fhn_tile<64>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
-        else
-          launch_fhn_tile<256>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+      int shape = 2;
+      if (force && force[0] >= '0' && force[0] <= '2') shape = (force[0] == '0') ? 0 : ((force[0] == '1') ? 2 : 1);
+      if (!A.normalize && (dx & 1) == 0 && dx >= 4 && shape != 0) {
+        if (shape == 2) {
+          if (npts / 4 <= 64)
+            launch_fhn_tile<2, 64>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+          else
+            launch_fhn_tile<2, 256>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+        } else {
+          if (npts / 2 <= 128)
+            launch_fhn_tile<1, 128>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+          else
+            launch_fhn_tile<1, 512>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+        }
       } else {
         launch_pde<FhnPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
       }

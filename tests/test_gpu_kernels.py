@@ -103,7 +103,7 @@ def test_rk_many_slices_both_step_conventions_vs_oracle():
 @pytest.mark.parametrize("d_x", [4, 6, 16, 18])
 def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
     """the 2x2-points-per-thread FHN kernel (csrc/rk.cu rk_fhn_tile_kernel) returns the bits of the
-    one-point-per-thread kernel (NNGP_RK_TILE=1 / 0 force one or the other), all RK methods, and both agree with
+    one-point-per-thread kernel and of the 1x2 variant (NNGP_RK_TILE forces each), all RK methods, and all agree with
     the NumPy oracle to 1e-12 scaled"""
     import os
     rng = np.random.default_rng(d_x)
@@ -115,13 +115,15 @@ def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
     for F, steps in (('RK8', 23), ('RK4', 11), ('RK2', 6), ('RK1', 5)):
         s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=steps, F=F, G='RK4')
         try:
-            os.environ["NNGP_RK_TILE"] = "1"
+            os.environ["NNGP_RK_TILE"] = "1"   # 2x2 blocks per thread
             got = s.run_F_batch(t0, t1, u0)
-            os.environ["NNGP_RK_TILE"] = "0"
+            os.environ["NNGP_RK_TILE"] = "2"   # 1x2 blocks per thread
+            got2 = s.run_F_batch(t0, t1, u0)
+            os.environ["NNGP_RK_TILE"] = "0"   # one point per thread
             ref = s.run_F_batch(t0, t1, u0)
         finally:
             del os.environ["NNGP_RK_TILE"]
-        assert np.array_equal(got, ref), F
+        assert np.array_equal(got, ref) and np.array_equal(got2, ref), F
         want = np.stack([ork.rk_last(o.f, F, t0[i], t1[i], steps, u0[i]) for i in range(n)])
         assert scaled_err(got, want) < 1e-12, F
 
