@@ -265,7 +265,7 @@ def main():
     fit_tf = flops_fit / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0
     roof_fit = {"kernel": "gp_fit_predict_kernel<20>", "bound": "fp64", "achieved": fit_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": fit_tf / fp64_peak if fp64_peak else None,
-                "traffic": 772608, "traffic_source": "profiles/r01/fit_r1b.summary.csv (dram read+write bytes per launch)",
+                "traffic": 279296, "traffic_source": "profiles/r01/fit_r1_final.summary.csv (dram read+write bytes per launch)",
                 "peak_source": peak_src,
                 "per_launch": {"launches": fit_n // args.steps, "avg_ms": fit_ms / max(fit_n, 1),
                                "nll_evals": nll_evals / max(fit_n, 1), "flops_per_eval": nll_flops(m)},
@@ -275,9 +275,9 @@ def main():
     fine_ms = sum(a.elapsed_time(b) for a, b in fine_events) / max(len(fine_events), 1)
     f_flops = rk_flops(d, 11) * args.fine_steps * math.ceil(N / world)
     rk_tf = f_flops / (fine_ms * 1e-3) / 1e12 if fine_ms > 0 else 0.0
-    roof_rk = {"kernel": "rk_fhn_tile_kernel<11,64>", "bound": "fp64", "achieved": rk_tf, "peak": fp64_peak,
+    roof_rk = {"kernel": "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": rk_tf, "peak": fp64_peak,
                "unit": "TFLOP/s", "frac": rk_tf / fp64_peak if fp64_peak else None,
-               "traffic": 2124544, "traffic_source": "profiles/r01/rk_r1d.summary.csv (dram read+write bytes per launch)",
+               "traffic": 2158336, "traffic_source": "profiles/r01/rk_tile_r1.summary.csv (dram read+write bytes per launch)",
                "peak_source": peak_src,
                "per_launch": {"launches": 1, "avg_ms": fine_ms, "slices": math.ceil(N / world),
                               "steps_per_slice": args.fine_steps, "flops_per_slice_step": rk_flops(d, 11)},
