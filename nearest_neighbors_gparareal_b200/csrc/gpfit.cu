@@ -407,6 +407,22 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
 #pragma unroll
   for (int k = 0; k < M; k++) {
     ok = ok && (p > pmin);  // failed factorisation (potf2: pivot <= 0 or NaN) -> +inf
+    // A search that starts where the kernel matrix is numerically singular sees +inf at every vertex;
+    // |inf - inf| = NaN never satisfies SciPy's fatol test, so it runs all maxfev = 400 evaluations
+    // (at the FHN target 14 % of the searches, 57 % of the evaluations, and the serial chain that ends
+    // the launch).  Near-duplicate neighbours fail at the first pivots: leave early at a few fixed
+    // steps (warp-uniform vote, so the shuffles below stay convergent).
+    if (!ALPHA && (k == 1 || k == 2 || k == 4 || k == 8 || k == 14) && k < M - 1) {
+      if (__any_sync(FULL, !ok)) {
+        GpOut bad;
+        bad.amp = amp;
+        bad.c = c;
+        bad.ok = false;
+        bad.val = dinf();
+        __syncwarp();  // the next evaluation overwrites the tile
+        return bad;
+      }
+    }
     const double ip = rcp_pos(p);
     const double w = a[k] * ip;  // l'_rk
     const double pk = p, zkk = zk;
