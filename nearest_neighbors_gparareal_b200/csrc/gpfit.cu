@@ -412,7 +412,11 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     // (at the FHN target 14 % of the searches, 57 % of the evaluations, and the serial chain that ends
     // the launch).  Near-duplicate neighbours fail at the first pivots: leave early at a few fixed
     // steps (warp-uniform vote, so the shuffles below stay convergent).
+#ifndef FIT_DENSE_CHECKS
     if (!ALPHA && (k == 1 || k == 2 || k == 4 || k == 8 || k == 14) && k < M - 1) {
+#else
+    if (!ALPHA && (k <= 6 || k == 8 || k == 11 || k == 14) && k >= 1 && k < M - 1) {
+#endif
       if (__any_sync(FULL, !ok)) {
         GpOut bad;
         bad.amp = amp;
@@ -670,7 +674,7 @@ __device__ __noinline__ double posterior_mean(double th0, double th1, double jit
 
 // registers per thread: 4-warp CTAs, K CTAs per SM
 #ifndef FIT_OCC20
-#define FIT_OCC20 2
+#define FIT_OCC20 3
 #endif
 template <int M> struct FitOcc { static constexpr int value = (M <= 12) ? 4 : ((M <= 20) ? FIT_OCC20 : 2); };
 
