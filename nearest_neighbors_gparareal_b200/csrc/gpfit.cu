@@ -264,6 +264,7 @@ template <int M>
 struct PairSlots {
   int oij[Tri<M>::NP];  // i*LD + j; an empty slot points at the unused diagonal element 0
   double r2[Tri<M>::NP];
+  double r2_10;  // squared distance of neighbours 1 and 0 (every lane): decides pivot 1
   bool pad[Tri<M>::NP];  // entry touches a padding row (m <= i < M) or slot empty: stored as 0
 };
 
@@ -282,6 +283,7 @@ __device__ __forceinline__ void pair_slots_init(PairSlots<M>& P, int lane, int m
     P.pad[t] = !valid || (i >= m);
     P.r2[t] = 0.0;
   }
+  P.r2_10 = 0.0;
 }
 
 // squared distances of the lane's entries for one query: r2 global [m*m] row-major
@@ -296,6 +298,7 @@ __device__ __forceinline__ void pair_slots_load(PairSlots<M>& P, const double* _
     }
     P.r2[t] = v;
   }
+  P.r2_10 = (m > 1) ? __ldg(r2 + m) : 0.0;
 }
 
 struct GpOut {
@@ -313,16 +316,53 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   double amp, inv;  // 10**sigma_y, 1/(10**sigma_x)
   exp10_pair(th1, -th0, amp, inv);
   const double c = -0.5 * inv;
-  // kernel entries of this lane + the diagonal exp(c*0) (NaN when c is not finite, as in NumPy),
-  // evaluated interleaved in groups of at most 8
-  double v[NP + 1];
+  // The matrix is factorised as K' = 2^-e0 K with e0 = the larger binary exponent of amp and jitter
+  // (an exact scaling: every pivot is scaled by the same power of two), so that the product of up to
+  // 16 pivots, each in (4 ulp, 4) after scaling, stays a normal number and log det K needs no
+  // per-pivot exponent bookkeeping.
+  const int e0 = min(1022, max((__double2hiint(amp) >> 20) & 0x7ff, (__double2hiint(jit10) >> 20) & 0x7ff) - 1023);
+  const double sc = __hiloint2double((1023 - e0) << 20, 0);
+  const double amp_s = amp * sc;
+  // First the diagonal exp(c*0) (NaN when c is not finite, as in NumPy) and the entry K_10 alone: they
+  // decide the first two pivots.  A search that starts where the kernel matrix is numerically singular
+  // sees +inf at every vertex; |inf - inf| = NaN never satisfies SciPy's fatol test, so it runs all
+  // maxfev = 400 evaluations (at the FHN target, whose neighbour rows become identical at the steady
+  // state, 14 % of the searches and 57 % of the evaluations), and nearly all of those fail at pivot 1.
+  // The test below computes pivots 0 and 1 with exactly the operations of the factorisation further
+  // down, so it only anticipates the decision (every lane holds the same values: uniform branch).
+  double dd0, pmin;
   {
-    constexpr int NV = NP + 1;
+    const double x2[2] = {c * P.r2_10, c * 0.0};
+    double e2[2];
+    exp_neg_vec<2>(x2, e2);
+    dd0 = fma(amp_s, e2[1], jit10 * sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
+    // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
+    // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
+    // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
+    // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
+    // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
+    pmin = dd0 * 8.8817841970012523e-16;
+    if (!ALPHA) {
+      const double k10 = (m > 1) ? amp_s * e2[0] : 0.0;
+      const double d1 = fma(-(k10 * rcp_pos(dd0)), k10, dd0);
+      if (__any_sync(FULL, !(dd0 > pmin) || !(d1 > pmin))) {
+        GpOut bad;
+        bad.amp = amp;
+        bad.c = c;
+        bad.ok = false;
+        bad.val = dinf();
+        return bad;
+      }
+    }
+  }
+  // kernel entries of this lane, evaluated interleaved in groups of at most 8
+  double v[NP];
+  {
+    constexpr int NV = NP;
     constexpr int G = (NV <= 8) ? NV : (NV + 1) / 2;
     double xin[NV];
 #pragma unroll
     for (int t = 0; t < NP; t++) xin[t] = c * P.r2[t];
-    xin[NP] = c * 0.0;
     {
       double xa[G], oa[G];
 #pragma unroll
@@ -341,14 +381,6 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       for (int t = 0; t < G2; t++) v[G + t] = oa[t];
     }
   }
-  // The matrix is factorised as K' = 2^-e0 K with e0 = the larger binary exponent of amp and jitter
-  // (an exact scaling: every pivot is scaled by the same power of two), so that the product of up to
-  // 16 pivots, each in (4 ulp, 4) after scaling, stays a normal number and log det K needs no
-  // per-pivot exponent bookkeeping.
-  const int e0 = min(1022, max((__double2hiint(amp) >> 20) & 0x7ff, (__double2hiint(jit10) >> 20) & 0x7ff) - 1023);
-  const double sc = __hiloint2double((1023 - e0) << 20, 0);
-  const double amp_s = amp * sc;
-  const double dd0 = fma(amp_s, v[NP], jit10 * sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
 #pragma unroll
   for (int t = 0; t < NP; t++) {  // unconditional stores: the exponentials above stay interleaved
     // only the lower triangle is stored: lane r never uses the entries right of its diagonal
@@ -389,12 +421,6 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     }
   };
   double dd = dd0;
-  // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
-  // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
-  // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
-  // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
-  // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
-  const double pmin = dd0 * 8.8817841970012523e-16;
   double z = rowvalid ? y : 0.0;
   double quad = 0.0, prod0 = 1.0, prod1 = 1.0;
   double inv_own = 1.0, w_own = 0.0;  // ALPHA: 1/d_r and (L'^-1 y)_r of the own row
