@@ -372,12 +372,17 @@ struct FhnPde {
     f[0] = (((m1 + v[0]) - (v[0] * v[0]) * v[0]) - v[1]) + A.p[5];
     f[1] = A.p[6] * ((m2 + v[0]) - v[1]);
   }
-  // Stage increment k_c = hs_c * f_c in 15 FP64 instructions per grid point and stage, coefficients
+  // Stage increment k_c = hs_c * f_c in 14 FP64 instructions per grid point and stage, coefficients
   // from the constant bank (q = derived parameters filled in by nngp_sys_args):
-  //   U = a_off S1 + u1 ((a_diag + 1) - u1^2) + (k - u2),   S = sum of the four neighbours
-  //   V = (b_off/tau) S2 + ((b_diag - 1)/tau) u2 + (1/tau) u1
+  //   hs0 U = hs0 (a_off S1 + u1 ((a_diag + 1) - u1^2) + (k - u2)),   S = sum of the four neighbours
+  //   hs1 V = (hs1 b_off/tau) S2 + (hs1 (b_diag - 1)/tau) u2 + (hs1/tau) u1   (hv = the three products, once per step)
+  __device__ static void step_coeffs(const SysArgs& A, double hs1, double (&hv)[3]) {
+    hv[0] = hs1 * A.q[1];
+    hv[1] = hs1 * A.q[2];
+    hv[2] = hs1 * A.p[6];
+  }
   __device__ void eval_k(const SysArgs& A, const double* buf, int p, const double (&v)[2],
-                         const double (&hs)[2], double (&k)[2]) const {
+                         const double (&hs)[2], const double (&hv)[3], double (&k)[2]) const {
     const double* b1 = buf;
     const double* b2 = buf + npts;
     const double s1 = (b1[pd] + b1[pl]) + (b1[pr] + b1[pu]);
@@ -385,7 +390,7 @@ struct FhnPde {
     const double t1 = fma(-v[0], v[0], A.q[0]);
     const double t2 = A.p[5] - v[1];
     k[0] = hs[0] * fma(A.p[2], s1, fma(v[0], t1, t2));
-    k[1] = hs[1] * fma(A.q[1], s2, fma(A.q[2], v[1], A.p[6] * v[0]));
+    k[1] = fma(hv[0], s2, fma(hv[1], v[1], hv[2] * v[0]));
   }
 };
 
@@ -408,8 +413,9 @@ struct BurgersPde {
     f[0] = fma(-v[0], adv, lap);  // Dxx@u - u*(Dx@u)
   }
   // k = hs (Dxx_off (ul + ur) + u (Dxx_diag - Dx_off (ur - ul)))
+  __device__ static void step_coeffs(const SysArgs&, double, double (&)[3]) {}
   __device__ void eval_k(const SysArgs& A, const double* buf, int p, const double (&v)[1],
-                         const double (&hs)[1], double (&k)[1]) const {
+                         const double (&hs)[1], const double (&)[3], double (&k)[1]) const {
     const double ul = buf[pl], ur = buf[pr];
     k[0] = hs[0] * fma(A.p[0], ul + ur, v[0] * fma(-A.p[2], ur - ul, A.p[1]));
   }
@@ -452,9 +458,10 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
   int par = 0;
   for (long long n = 0; n < steps; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
-    double hs[NC];
+    double hs[NC], hv[3];
 #pragma unroll
     for (int c = 0; c < NC; c++) hs[c] = NORM ? h * sc[c] : h;
+    RHS::step_coeffs(A, hs[NC - 1], hv);
 #pragma unroll
     for (int i = 0; i < S; i++) {
       double v[NC], f[NC];
@@ -470,7 +477,7 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
         if (active) buf[c * npts + p] = v[c];
       }
       __syncthreads();
-      rhs.eval_k(A, buf, pp, v, hs, f);
+      rhs.eval_k(A, buf, pp, v, hs, hv, f);
 #pragma unroll
       for (int c = 0; c < NC; c++) k[c][i] = f[c];
     }
@@ -536,6 +543,8 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
   int par = 0;
   for (long long n = 0; n < steps; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
+    double hv[3];
+    FhnPde::step_coeffs(A, h, hv);
 #pragma unroll
     for (int i = 0; i < S; i++) {
       double* buf = sm + par * (2 * npts);
@@ -579,7 +588,7 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
         const double e1 = fma(-v0, v0, A.q[0]);
         const double e2 = A.p[5] - v1;
         k[0][q][i] = h * fma(A.p[2], sn[0][q], fma(v0, e1, e2));
-        k[1][q][i] = h * fma(A.q[1], sn[1][q], fma(A.q[2], v1, A.p[6] * v0));
+        k[1][q][i] = fma(hv[0], sn[1][q], fma(hv[1], v1, hv[2] * v0));
       }
     }
 #pragma unroll
