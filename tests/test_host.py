@@ -191,3 +191,28 @@ def test_time_slice_sharding_all_gather_gloo_world2(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port]) for r in range(2)]
     codes = [p.wait(timeout=180) for p in procs]
     assert codes == [0, 0]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port on the host cores) prints ONE JSON
+    line with the contract keys; small workload so that it runs in seconds on CPU.  Under torchrun only rank 0
+    prints (checked through the RANK environment variable)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--dx", "4", "--slices", "16", "--fine-steps", "50"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "iters/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["N_slices"] == 16 and line["config"]["d"] == 32
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
