@@ -406,18 +406,26 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   // one batch.  Every lane sees every pivot d_k and (L'^-1 y)_k, so  y^T K^-1 y = sum w_k^2 / d_k  and
   // log det K = log prod d_k (mantissa product + exponent sum) are accumulated redundantly in all
   // lanes: no warp reduction, one logarithm.
-  auto load_col = [&](int k, double (&u)[M]) {
+#ifdef FIT_NO_PREFETCH
+  constexpr bool PREFETCH = false;  // experiment: fewer registers (more warps per SM), column read where used
+#else
+  constexpr bool PREFETCH = true;
+#endif
+  constexpr int PREFETCH_M = PREFETCH ? M : 2;
+  auto load_col = [&](int k, double (&u)[PREFETCH_M]) {
     // u[j] = column k entry of row j (unscaled), j > k; uniform addresses -> broadcast loads
-    int j = k + 1;
-    if (j < M && (j & 1)) {
-      u[j] = Kt[k * LD + j];
-      j++;
-    }
+    if constexpr (PREFETCH) {
+      int j = k + 1;
+      if (j < M && (j & 1)) {
+        u[j] = Kt[k * LD + j];
+        j++;
+      }
 #pragma unroll
-    for (; j + 1 < M; j += 2) {
-      const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
-      u[j] = u2.x;
-      u[j + 1] = u2.y;
+      for (; j + 1 < M; j += 2) {
+        const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
+        u[j] = u2.x;
+        u[j + 1] = u2.y;
+      }
     }
   };
   double dd = dd0;
@@ -425,11 +433,11 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   double quad = 0.0, prod0 = 1.0, prod1 = 1.0;
   double inv_own = 1.0, w_own = 0.0;  // ALPHA: 1/d_r and (L'^-1 y)_r of the own row
   bool ok = true;
-  double u[M];
+  double u[PREFETCH_M];
   double p = shfl(dd, 0), zk = shfl(z, 0);
   if (lane > 0 && lane < M) Kt[lane] = a[0];
   __syncwarp();
-  load_col(0, u);
+  if constexpr (PREFETCH) load_col(0, u);
 #pragma unroll
   for (int k = 0; k < M; k++) {
     ok = ok && (p > pmin);  // failed factorisation (potf2: pivot <= 0 or NaN) -> +inf
@@ -463,16 +471,31 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     dd = fma(-w, a[k], dd);
     z = fma(-w, zk, z);
     if (k + 1 < M) {
-      a[k + 1] = fma(-w, u[k + 1], a[k + 1]);
+      a[k + 1] = fma(-w, PREFETCH ? u[(PREFETCH ? k + 1 : 0)] : Kt[k * LD + k + 1], a[k + 1]);
       p = shfl(dd, k + 1);
       zk = shfl(z, k + 1);
       if (k + 2 < M) {
         if (lane > k + 1 && lane < M) Kt[(k + 1) * LD + lane] = a[k + 1];
         __syncwarp();
       }
+      if constexpr (PREFETCH) {
 #pragma unroll
-      for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
-      if (k + 2 < M) load_col(k + 1, u);
+        for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
+        if (k + 2 < M) load_col(k + 1, u);
+      } else {
+        // column k was stored before the previous __syncwarp pair; rows differ per step, no hazard
+        int j = k + 2;
+        if (j < M && (j & 1)) {
+          a[j] = fma(-w, Kt[k * LD + j], a[j]);
+          j++;
+        }
+#pragma unroll
+        for (; j + 1 < M; j += 2) {
+          const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
+          a[j] = fma(-w, u2.x, a[j]);
+          a[j + 1] = fma(-w, u2.y, a[j + 1]);
+        }
+      }
     }
     if (!ALPHA) {  // off the critical path; a padding row has z = 0 and is left out of the determinant
       quad = fma(zkk * zkk, ip, quad);
