@@ -224,9 +224,58 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
 
+// padding entries carry the index INT64_MAX and sort after every real key (NaN distances included)
+__device__ __forceinline__ bool key_less_pad(double d1, long long i1, double d2, long long i2) {
+  const long long IMAX = 0x7fffffffffffffffLL;
+  if (i1 == IMAX) return false;
+  if (i2 == IMAX) return true;
+  return key_less(d1, i1, d2, i2);
+}
+
+// bitonic sort of one key per lane, ascending over the lanes
+__device__ __forceinline__ void warp_sort32(double& d, long long& i, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, d, j);
+      const long long oi = __shfl_xor_sync(0xffffffffu, i, j);
+      const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+      const bool less = key_less_pad(od, oi, d, i);
+      if (take_min == less) {
+        d = od;
+        i = oi;
+      }
+    }
+  }
+}
+
+// (d, i): a sorted list per lane; (bd, bi): another sorted list.  Leaves the 32 smallest of the union, sorted.
+__device__ __forceinline__ void warp_merge32(double& d, long long& i, double bd, long long bi, int lane) {
+  const double rd = shfl_d(bd, 31 - lane);
+  const long long ri = shfl_ll(bi, 31 - lane);
+  if (key_less_pad(rd, ri, d, i)) {  // elementwise minimum against the reversed list: a bitonic sequence
+    d = rd;
+    i = ri;
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d, j);
+    const long long oi = __shfl_xor_sync(0xffffffffu, i, j);
+    const bool less = key_less_pad(od, oi, d, i);
+    if (((lane & j) == 0) == less) {
+      d = od;
+      i = oi;
+    }
+  }
+}
+
 // Top-m of the keys (dist[i], id(i)), i in this CTA's chunk of [0, n): id(i) = in_idx[i] when in_idx is
 // given (second level: merging the per-chunk candidates), else i.  Grid (chunks, queries); each CTA writes
 // m sorted (distance, index) pairs, padded with (+inf, INT64_MAX) when the chunk holds fewer.
+// Every warp keeps a sorted list of its m best over the lanes.  A round of 32 candidates is tested against the
+// list's m-th key; a few survivors are inserted one by one (ballot + shuffle), many (the first rounds) are
+// sorted by a bitonic network and merged.  Warp 0 then merges the warps' lists.
 __global__ void __launch_bounds__(KNN_SEL_THREADS)
 select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_idx, long long n,
               long long chunk, int m, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
@@ -240,7 +289,7 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
   const long long lo = (long long)blockIdx.x * chunk, hi = min(n, lo + chunk);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const long long IMAX = 0x7fffffffffffffffLL;
-  // lane l holds the l-th smallest key seen by this warp (l < m)
+  // lane l holds the l-th smallest key seen by this warp (l < m), padding beyond
   double bd = INF;
   long long bi = IMAX;
   for (long long base = lo + (long long)w * 32; base < hi; base += KNN_SEL_THREADS) {
@@ -253,13 +302,28 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
     }
     const double td = shfl_d(bd, m - 1);
     const long long ti = shfl_ll(bi, m - 1);
-    unsigned pending = __ballot_sync(0xffffffffu, (cidx != IMAX) && key_less(c, cidx, td, ti));
+    const bool want = key_less_pad(c, cidx, td, ti);
+    unsigned pending = __ballot_sync(0xffffffffu, want);
+    if (pending == 0) continue;
+    if (__popc(pending) > 3) {
+      if (!want) {
+        c = INF;
+        cidx = IMAX;
+      }
+      warp_sort32(c, cidx, lane);
+      warp_merge32(bd, bi, c, cidx, lane);
+      if (lane >= m) {
+        bd = INF;
+        bi = IMAX;
+      }
+      continue;
+    }
     while (pending) {
       const int src = __ffs(pending) - 1;
       pending &= pending - 1;
       const double xd = shfl_d(c, src);
       const long long xi = shfl_ll(cidx, src);
-      const unsigned below = __ballot_sync(0xffffffffu, (lane < m) && key_less(bd, bi, xd, xi));
+      const unsigned below = __ballot_sync(0xffffffffu, (lane < m) && key_less_pad(bd, bi, xd, xi));
       const int pos = __popc(below);
       const double ud = __shfl_up_sync(0xffffffffu, bd, 1);
       const long long ui = __shfl_up_sync(0xffffffffu, bi, 1);
@@ -272,28 +336,28 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
           bi = xi;
         }
       }
+      if (lane >= m) {
+        bd = INF;
+        bi = IMAX;
+      }
     }
   }
-  cd[w * 32 + lane] = (lane < m) ? bd : INF;
-  ci[w * 32 + lane] = (lane < m) ? bi : IMAX;
+  cd[w * 32 + lane] = bd;
+  ci[w * 32 + lane] = bi;
   __syncthreads();
-  // merge by ranking: all real keys are distinct (unique index), so ranks are unique
-  const long long ob = ((long long)q * gridDim.x + blockIdx.x) * m;
-  const double md = cd[threadIdx.x];
-  const long long mi = ci[threadIdx.x];
-  int nreal = 0;
-  for (int t = 0; t < NW * 32; t++) nreal += (ci[t] != IMAX) ? 1 : 0;
-  if (mi != IMAX) {
-    int rank = 0;
-    for (int t = 0; t < NW * 32; t++) rank += key_less(cd[t], ci[t], md, mi) ? 1 : 0;
-    if (rank < m) {
-      idx_out[ob + rank] = mi;
-      dist_out[ob + rank] = md;
+  if (w != 0) return;
+#pragma unroll 1
+  for (int o = 1; o < NW; o++) {
+    warp_merge32(bd, bi, cd[o * 32 + lane], ci[o * 32 + lane], lane);
+    if (lane >= m) {
+      bd = INF;
+      bi = IMAX;
     }
   }
-  if ((int)threadIdx.x < m && (int)threadIdx.x >= nreal) {  // chunk with fewer than m rows: padding
-    idx_out[ob + threadIdx.x] = IMAX;
-    dist_out[ob + threadIdx.x] = INF;
+  if (lane < m) {
+    const long long ob = ((long long)q * gridDim.x + blockIdx.x) * m;
+    idx_out[ob + lane] = bi;
+    dist_out[ob + lane] = (bi == IMAX) ? INF : bd;
   }
 }
 
