@@ -292,13 +292,27 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
   // lane l holds the l-th smallest key seen by this warp (l < m), padding beyond
   double bd = INF;
   long long bi = IMAX;
+  // the next round's candidate is loaded while the current one is processed
+  double cn = INF;
+  long long cnidx = IMAX;
+  {
+    const long long i0 = lo + (long long)w * 32 + lane;
+    if (i0 < hi) {
+      cn = dq[i0];
+      cnidx = iq ? iq[i0] : i0;
+    }
+  }
   for (long long base = lo + (long long)w * 32; base < hi; base += KNN_SEL_THREADS) {
-    const long long i = base + lane;
-    double c = INF;
-    long long cidx = IMAX;
-    if (i < hi) {
-      c = dq[i];
-      cidx = iq ? iq[i] : i;
+    double c = cn;
+    long long cidx = cnidx;
+    {
+      const long long i1 = base + KNN_SEL_THREADS + lane;
+      cn = INF;
+      cnidx = IMAX;
+      if (i1 < hi) {
+        cn = dq[i1];
+        cnidx = iq ? iq[i1] : i1;
+      }
     }
     const double td = shfl_d(bd, m - 1);
     const long long ti = shfl_ll(bi, m - 1);
@@ -361,15 +375,16 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
   }
 }
 
-static constexpr long long KNN_CHUNK = 4096;  // least rows per first-level selection CTA
+static constexpr long long KNN_CHUNK = 4096;  // rows up to which one CTA selects alone; chunks are >= a quarter of it
 
 // Rows per first-level CTA: the scan of one query is split only as far as it takes to fill the GPU
 // (about two CTAs per SM over all queries) -- every CTA pays the fill of its own top-m lists, so
 // with many queries one CTA per query is the faster arrangement.
 static long long knn_chunk_rows(int nq, long long n) {
+  if (n <= KNN_CHUNK) return n;  // one CTA per query (the sweep's case)
   const long long want = (296 + nq - 1) / nq;  // CTAs per query
   long long chunk = (n + want - 1) / want;
-  if (chunk < KNN_CHUNK) chunk = KNN_CHUNK;
+  if (chunk < KNN_CHUNK / 4) chunk = KNN_CHUNK / 4;
   return chunk;
 }
 
