@@ -381,7 +381,7 @@ static constexpr long long KNN_CHUNK = 4096;  // rows up to which one CTA select
 // (about two CTAs per SM over all queries) -- every CTA pays the fill of its own top-m lists, so
 // with many queries one CTA per query is the faster arrangement.
 static long long knn_chunk_rows(int nq, long long n) {
-  if (n <= KNN_CHUNK) return n;  // one CTA per query (the sweep's case)
+  if (n <= KNN_CHUNK) return n > 0 ? n : 1;  // one CTA per query (the sweep's case)
   const long long want = (296 + nq - 1) / nq;  // CTAs per query
   long long chunk = (n + want - 1) / want;
   if (chunk < KNN_CHUNK / 4) chunk = KNN_CHUNK / 4;
