@@ -216,9 +216,10 @@ def main():
         h.dataset_reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        par.device_fine_step(st)  # the batched RK8 launch on torch's current stream (+ the all-gather for N>1)
+        l0 = h.launch_count()
+        par.device_fine_step(st)  # the batched RK8 launches on torch's current stream (+ the all-gather for N>1)
         e1.record()
-        fine_events.append((e0, e1))
+        fine_events.append((e0, e1, h.launch_count() - l0))
         par.device_sweep(st, 0, starts=starts)
         return par.device_errors(st)  # the one device->host read of an iteration (N+1 doubles)
 
@@ -272,15 +273,19 @@ def main():
                 "share_of_step": fit_ms / (ms_step * args.steps),
                 "note": "latency-bound: 14% of the searches run to SciPy's maxfev=400, a launch lasts as long as its "
                         "longest serial chain of evaluations (DESIGN.md 4.5)"}
-    fine_ms = sum(a.elapsed_time(b) for a, b in fine_events) / max(len(fine_events), 1)
+    fine_ms = sum(a.elapsed_time(b) for a, b, _ in fine_events) / max(len(fine_events), 1)
+    fine_launches = max(1, fine_events[-1][2]) if fine_events else 1
     f_flops = rk_flops(d, 11) * args.fine_steps * math.ceil(N / world)
     rk_tf = f_flops / (fine_ms * 1e-3) / 1e12 if fine_ms > 0 else 0.0
     roof_rk = {"kernel": "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": rk_tf, "peak": fp64_peak,
                "unit": "TFLOP/s", "frac": rk_tf / fp64_peak if fp64_peak else None,
                "traffic": 2158336, "traffic_source": "profiles/r01/rk_tile_r1.summary.csv (dram read+write bytes per launch)",
                "peak_source": peak_src,
-               "per_launch": {"launches": 1, "avg_ms": fine_ms, "slices": math.ceil(N / world),
-                              "steps_per_slice": args.fine_steps, "flops_per_slice_step": rk_flops(d, 11)},
+               "per_launch": {"launches": fine_launches, "avg_ms": fine_ms / fine_launches,
+                              "flops": f_flops / fine_launches, "fine_step_ms": fine_ms, "slices": math.ceil(N / world),
+                              "steps_per_slice": args.fine_steps, "flops_per_slice_step": rk_flops(d, 11),
+                              "note": "the fine step is a sequence of balanced launches over (chunk of steps, slice) "
+                                      "tasks, 2 CTAs per SM (csrc/rk.cu launch_fhn_tile_s)"},
                "share_of_step": fine_ms / ms_step}
     roofline, other = (roof_rk, roof_fit) if roof_rk["share_of_step"] >= roof_fit["share_of_step"] else (roof_fit, roof_rk)
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] // args.steps} for k, v in prof.items()}

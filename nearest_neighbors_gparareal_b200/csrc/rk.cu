@@ -512,10 +512,17 @@ struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) :
 
 template <int S, int TY, int TB>
 __global__ void __launch_bounds__(TB, TileOcc<TY, TB>::value)
-rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__ t0s,
-                   const double* __restrict__ t1s, const double* __restrict__ u0, long long ld0,
-                   double* __restrict__ u1, long long ld1) {
+rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long long task0, int n_chunks,
+                   const double* __restrict__ t0s, const double* __restrict__ t1s,
+                   const double* __restrict__ u0, long long ld0, double* __restrict__ u1, long long ld1) {
   constexpr int NV = 2 * TY;  // points per thread, row-major inside the block
+  // task = (chunk of the step range, slice): chunk c of a slice continues from u1 where chunk c-1 (an
+  // earlier launch) left it -- see launch_fhn_tile
+  const long long task = task0 + blockIdx.x;
+  if (task >= (long long)n_slices * n_chunks) return;
+  const int chunk = (int)(task / n_slices);
+  const long long s = task - (long long)chunk * n_slices;
+  const long long n_begin = (steps * chunk) / n_chunks, n_end = (steps * (chunk + 1)) / n_chunks;
   extern __shared__ double sm[];
   const Tableau& T = c_tab[SlotOf<S>::value];
   const int dx = (int)A.p[0], npts = dx * dx, hx = dx >> 1, ntile = hx * (dx / TY);
@@ -527,11 +534,10 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
   const int odn = ((iy0 + TY == dx) ? 0 : iy0 + TY) * dx + ix0;  // row iy0+TY
   const int xl = (ix0 == 0 ? dx : ix0) - 1, xr = (ix0 + 2 == dx) ? 0 : ix0 + 2;
   const int ol0 = iy0 * dx + xl, or0 = iy0 * dx + xr;
-  const long long s = blockIdx.x;
   double u[2][NV], k[2][NV][S];
 #pragma unroll
   for (int c = 0; c < 2; c++) {
-    const double* src = u0 + s * ld0 + c * npts;
+    const double* src = ((chunk == 0) ? u0 + s * ld0 : u1 + s * ld1) + c * npts;
 #pragma unroll
     for (int r = 0; r < TY; r++) {
       u[c][2 * r] = src[o00 + r * dx];
@@ -541,7 +547,7 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
   int par = 0;
-  for (long long n = 0; n < steps; n++) {
+  for (long long n = n_begin; n < n_end; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
     double hv[3];
     FhnPde::step_coeffs(A, h, hv);
@@ -612,17 +618,58 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, const double* __restr
   }
 }
 
-template <int TY, int TB>
-static void launch_fhn_tile(const SysArgs& A, int npts, int method, int h_mode, long long steps, int n,
-                            const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
-                            long long ld1, cudaStream_t st) {
+// Time-chunked launch.  Measured (profiles/r01/rk_sweep.log): an SM reaches its full fine-step throughput
+// with TWO resident slices (one warp per sub-partition, each saturating its FP64 issue); 3 slices per SM are
+// slower than 2 (two sub-partitions hold two warps), 4 gain nothing, and 512 slices on 148 SMs leave 80 SMs
+// a slice short.  So when a GPU holds more than 2 slices per SM the step range is cut into chunks and the
+// (chunk, slice) tasks are executed chunk-major by a sequence of launches of exactly 2 CTAs per SM (forced by
+// the shared-memory request): every launch is perfectly balanced, a slice's state passes from chunk to chunk
+// through u1, and task (c, s) always falls into a later launch than (c-1, s) because a launch is smaller than
+// the number of slices.  Results are bit-identical to the single launch.
+template <int S, int TY, int TB>
+static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long steps, int n, int sms,
+                             const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
+                             long long ld1, cudaStream_t st) {
   const int threads = ((npts / (2 * TY) + 31) / 32) * 32;
   const size_t smem = 2 * sizeof(double) * 2 * npts;
+  const int per_launch = 2 * sms;
+  const char* force = getenv("NNGP_RK_CHUNKS");  // experiments: 0 = never chunk
+  if (TB > 64 || n <= per_launch || steps < 4096 || (force && force[0] == '0')) {
+    rk_fhn_tile_kernel<S, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
+    return 1;
+  }
+  // chunks: the smallest count >= 24 that fills the last launch, else 32
+  int chunks = 32;
+  for (int c = 24; c <= 64; c++)
+    if (((long long)n * c) % per_launch == 0) {
+      chunks = c;
+      break;
+    }
+  const size_t smem2 = 80 * 1024;  // > 1/3 of the SM's shared memory: at most two CTAs per SM
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(rk_fhn_tile_kernel<S, TY, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    attr_set = true;
+  }
+  const long long total = (long long)n * chunks;
+  int launches = 0;
+  for (long long task0 = 0; task0 < total; task0 += per_launch) {
+    const int grid = (int)((total - task0 < per_launch) ? total - task0 : per_launch);
+    rk_fhn_tile_kernel<S, TY, TB><<<grid, threads, smem2, st>>>(A, h_mode, steps, n, task0, chunks, t0, t1, u0, ld0, u1, ld1);
+    launches++;
+  }
+  return launches;
+}
+
+template <int TY, int TB>
+static int launch_fhn_tile(const SysArgs& A, int npts, int method, int h_mode, long long steps, int n, int sms,
+                           const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
+                           long long ld1, cudaStream_t st) {
   switch (method) {
-    case 1: rk_fhn_tile_kernel<1, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 2: rk_fhn_tile_kernel<2, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    case 4: rk_fhn_tile_kernel<4, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
-    default: rk_fhn_tile_kernel<11, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, t0, t1, u0, ld0, u1, ld1); break;
+    case 1: return launch_fhn_tile_s<1, TY, TB>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
+    case 2: return launch_fhn_tile_s<2, TY, TB>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
+    case 4: return launch_fhn_tile_s<4, TY, TB>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
+    default: return launch_fhn_tile_s<11, TY, TB>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
   }
 }
 
@@ -777,17 +824,21 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
       int shape = 2;
       if (force && force[0] >= '0' && force[0] <= '2') shape = (force[0] == '0') ? 0 : ((force[0] == '1') ? 2 : 1);
       if (!A.normalize && (dx & 1) == 0 && dx >= 4 && shape != 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        int nl = 1;
         if (shape == 2) {
           if (npts / 4 <= 64)
-            launch_fhn_tile<2, 64>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+            nl = launch_fhn_tile<2, 64>(A, npts, method, h_mode, steps, n_slices, sms, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
           else
-            launch_fhn_tile<2, 256>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+            nl = launch_fhn_tile<2, 256>(A, npts, method, h_mode, steps, n_slices, sms, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
         } else {
           if (npts / 2 <= 128)
-            launch_fhn_tile<1, 128>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+            nl = launch_fhn_tile<1, 128>(A, npts, method, h_mode, steps, n_slices, sms, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
           else
-            launch_fhn_tile<1, 512>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
+            nl = launch_fhn_tile<1, 512>(A, npts, method, h_mode, steps, n_slices, sms, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
         }
+        h->launches += nl - 1;
       } else {
         launch_pde<FhnPde>(A, npts, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st);
       }

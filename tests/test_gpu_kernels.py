@@ -128,6 +128,28 @@ def test_fhn_tile_kernel_equals_point_kernel_bitwise(d_x):
         assert scaled_err(got, want) < 1e-12, F
 
 
+def test_fhn_time_chunked_fine_step_equals_single_launch_bitwise():
+    """more than two slices per SM and a long step range: the fine step is executed as a sequence of balanced
+    launches over (chunk of steps, slice) tasks (csrc/rk.cu launch_fhn_tile_s); NNGP_RK_CHUNKS=0 forces the single
+    launch.  Same bits, both step-size conventions, slice count not a multiple of the launch size."""
+    import os
+    rng = np.random.default_rng(11)
+    ode = nn.FHN_PDE(d_x=4)
+    n = 333
+    u0 = ode.get_init_cond()[None, :] + 0.01 * rng.standard_normal((n, 32))
+    t0 = rng.uniform(0, 1, n)
+    t1 = t0 + rng.uniform(0.5, 1.5, n)
+    for h_mode in ("linspace", "const"):
+        s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=4999, F='RK8', G='RK4', h_mode=h_mode)
+        got = s.run_F_batch(t0, t1, u0)
+        try:
+            os.environ["NNGP_RK_CHUNKS"] = "0"
+            ref = s.run_F_batch(t0, t1, u0)
+        finally:
+            del os.environ["NNGP_RK_CHUNKS"]
+        assert np.all(np.isfinite(got)) and np.array_equal(got, ref), h_mode
+
+
 def test_rk_errors(handle):
     ode = nn.Burgers(d_x=2000, normalization='-11')
     s = nn.CudaSolverRK(ode.get_vector_field(), Ng=1, Nf=1, F='RK4', G='RK1')
