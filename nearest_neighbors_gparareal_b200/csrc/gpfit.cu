@@ -27,6 +27,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 static constexpr int GP_WARPS = 4;  // warps per CTA of the persistent fit kernel
 static constexpr unsigned FULL = 0xffffffffu;
@@ -301,6 +302,44 @@ __device__ __forceinline__ void pair_slots_load(PairSlots<M>& P, const double* _
   P.r2_10 = (m > 1) ? __ldg(r2 + m) : 0.0;
 }
 
+// Hyper-parameter transforms, scaling and the first two pivots -- everything that depends on (theta, jitter)
+// and the single squared distance r2_10 only.  Arguments may differ from lane to lane (the Nelder-Mead loop
+// evaluates the heads of four candidate points at once); gp_core calls it with warp-uniform arguments.
+struct GpHead {
+  double amp, c, sc, amp_s, dd0, pmin;
+  bool fail01;  // pivot 0 or pivot 1 fails: the objective is +inf whatever the rest of the matrix holds
+};
+
+__device__ __forceinline__ GpHead gp_head(double th0, double th1, double jit10, double r2_10, int m) {
+  GpHead g;
+  double inv;  // amp = 10**sigma_y, inv = 1/(10**sigma_x)
+  exp10_pair(th1, -th0, g.amp, inv);
+  g.c = -0.5 * inv;
+  // The matrix is factorised as K' = 2^-e0 K with e0 = the larger binary exponent of amp and jitter
+  // (an exact scaling: every pivot is scaled by the same power of two), so that the product of up to
+  // 16 pivots, each in (4 ulp, 4) after scaling, stays a normal number and log det K needs no
+  // per-pivot exponent bookkeeping.
+  const int e0 = min(1022, max((__double2hiint(g.amp) >> 20) & 0x7ff, (__double2hiint(jit10) >> 20) & 0x7ff) - 1023);
+  g.sc = __hiloint2double((1023 - e0) << 20, 0);
+  g.amp_s = g.amp * g.sc;
+  // the diagonal exp(c*0) (NaN when c is not finite, as in NumPy) and the entry K_10
+  const double x2[2] = {g.c * r2_10, g.c * 0.0};
+  double e2[2];
+  exp_neg_vec<2>(x2, e2);
+  g.dd0 = fma(g.amp_s, e2[1], jit10 * g.sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
+  // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
+  // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
+  // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
+  // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
+  // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
+  g.pmin = g.dd0 * 8.8817841970012523e-16;
+  // pivots 0 and 1 with exactly the operations of the factorisation in gp_core
+  const double k10 = (m > 1) ? g.amp_s * e2[0] : 0.0;
+  const double d1 = fma(-(k10 * rcp_pos(g.dd0)), k10, g.dd0);
+  g.fail01 = !(g.dd0 > g.pmin) || !(d1 > g.pmin);
+  return g;
+}
+
 struct GpOut {
   double val, amp, c;
   bool ok;
@@ -313,46 +352,21 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   static_assert(M % 2 == 0, "M even: 16-byte loads of column pairs");
   constexpr int LD = Tri<M>::LD;
   constexpr int NP = Tri<M>::NP;
-  double amp, inv;  // 10**sigma_y, 1/(10**sigma_x)
-  exp10_pair(th1, -th0, amp, inv);
-  const double c = -0.5 * inv;
-  // The matrix is factorised as K' = 2^-e0 K with e0 = the larger binary exponent of amp and jitter
-  // (an exact scaling: every pivot is scaled by the same power of two), so that the product of up to
-  // 16 pivots, each in (4 ulp, 4) after scaling, stays a normal number and log det K needs no
-  // per-pivot exponent bookkeeping.
-  const int e0 = min(1022, max((__double2hiint(amp) >> 20) & 0x7ff, (__double2hiint(jit10) >> 20) & 0x7ff) - 1023);
-  const double sc = __hiloint2double((1023 - e0) << 20, 0);
-  const double amp_s = amp * sc;
-  // First the diagonal exp(c*0) (NaN when c is not finite, as in NumPy) and the entry K_10 alone: they
-  // decide the first two pivots.  A search that starts where the kernel matrix is numerically singular
-  // sees +inf at every vertex; |inf - inf| = NaN never satisfies SciPy's fatol test, so it runs all
-  // maxfev = 400 evaluations (at the FHN target, whose neighbour rows become identical at the steady
-  // state, 14 % of the searches and 57 % of the evaluations), and nearly all of those fail at pivot 1.
-  // The test below computes pivots 0 and 1 with exactly the operations of the factorisation further
-  // down, so it only anticipates the decision (every lane holds the same values: uniform branch).
-  double dd0, pmin;
-  {
-    const double x2[2] = {c * P.r2_10, c * 0.0};
-    double e2[2];
-    exp_neg_vec<2>(x2, e2);
-    dd0 = fma(amp_s, e2[1], jit10 * sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
-    // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
-    // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
-    // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
-    // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
-    // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
-    pmin = dd0 * 8.8817841970012523e-16;
-    if (!ALPHA) {
-      const double k10 = (m > 1) ? amp_s * e2[0] : 0.0;
-      const double d1 = fma(-(k10 * rcp_pos(dd0)), k10, dd0);
-      if (__any_sync(FULL, !(dd0 > pmin) || !(d1 > pmin))) {
-        GpOut bad;
-        bad.amp = amp;
-        bad.c = c;
-        bad.ok = false;
-        bad.val = dinf();
-        return bad;
-      }
+  // A search that starts where the kernel matrix is numerically singular sees +inf at every vertex;
+  // |inf - inf| = NaN never satisfies SciPy's fatol test, so it runs all maxfev = 400 evaluations (at the
+  // FHN target, whose neighbour rows become identical at the steady state, 14 % of the searches and 57 % of
+  // the evaluations), and nearly all of those fail at pivot 1: decided by the head alone, before the
+  // matrix is built (every lane holds the same values: uniform branch).
+  const GpHead hd = gp_head(th0, th1, jit10, P.r2_10, m);
+  const double amp = hd.amp, c = hd.c, sc = hd.sc, amp_s = hd.amp_s, dd0 = hd.dd0, pmin = hd.pmin;
+  if (!ALPHA) {
+    if (__any_sync(FULL, hd.fail01)) {
+      GpOut bad;
+      bad.amp = amp;
+      bad.c = c;
+      bad.ok = false;
+      bad.val = dinf();
+      return bad;
     }
   }
   // kernel entries of this lane, evaluated interleaved in groups of at most 8
@@ -514,6 +528,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     const int h0 = __double2hiint(prod0), h1 = __double2hiint(prod1);
     const double m0 = __hiloint2double((h0 & 0x000fffff) | 0x3ff00000, __double2loint(prod0));
     const double m1 = __hiloint2double((h1 & 0x000fffff) | 0x3ff00000, __double2loint(prod1));
+    const int e0 = 1023 - ((__double2hiint(sc) >> 20) & 0x7ff);  // sc = 2^-e0
     const int esum = (h0 >> 20) + (h1 >> 20) - 2046 + m * e0;
     const double res = fma(0.5, fma(quad, sc, log_pos_plus(m0 * m1, esum)), hml);
     o.val = (ok && res == res) ? res : dinf();
@@ -572,7 +587,7 @@ __device__ __forceinline__ double shrink_to(double x0, double xj) {
 template <int M>
 __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10, double fatol, double xatol,
                                              const PairSlots<M>& P, double y, int m, int lane,
-                                             double* __restrict__ Lt, double hml) {
+                                             double* __restrict__ Lt, double hml, bool head_batch) {
   const int maxfun = 400, maxiter = 400;  // 200 * N
   double sx[3][2], sf[3];
   sx[0][0] = s0; sx[0][1] = s1;
@@ -582,8 +597,19 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
   int fcalls = 0, it = 1, phase = PH_INIT0;
   double p0 = s0, p1 = s1;
   double xb0 = 0, xb1 = 0, xr0 = 0, xr1 = 0, fxr = 0;
+  // When every vertex is +inf an iteration evaluates the reflection, the inside contraction and the two shrunk
+  // vertices -- four points known in advance.  Their heads (gp_head: do pivots 0 / 1 fail?) are computed at
+  // once in four lanes; an evaluation whose point is in this list with a failing head returns +inf without
+  // being repeated.  Same arithmetic, same decisions, a quarter of the work for the searches that run to maxfev.
+  double cx0[4], cx1[4];
+  unsigned cmask = 0;
   for (;;) {
-    const double f = gp_core<M, false>(p0, p1, jit10, P, y, m, lane, Lt, hml).val;
+    bool hit = false;
+    if (cmask) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) hit = hit || (((cmask >> j) & 1u) && p0 == cx0[j] && p1 == cx1[j]);
+    }
+    const double f = hit ? dinf() : gp_core<M, false>(p0, p1, jit10, P, y, m, lane, Lt, hml).val;
     fcalls++;
     bool aborted = false, do_shrink = false;
     if (phase == PH_INIT0) {
@@ -674,6 +700,18 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
     xr0 = __dsub_rn(__dmul_rn(2.0, xb0), sx[2][0]);
     xr1 = __dsub_rn(__dmul_rn(2.0, xb1), sx[2][1]);
     phase = PH_REFLECT; p0 = xr0; p1 = xr1;
+    cmask = 0;
+    if (head_batch && sf[0] == dinf()) {  // sorted: the best vertex is +inf, so all are
+      cx0[0] = xr0; cx1[0] = xr1;
+      cx0[1] = __dadd_rn(__dmul_rn(0.5, xb0), __dmul_rn(0.5, sx[2][0]));  // inside contraction
+      cx1[1] = __dadd_rn(__dmul_rn(0.5, xb1), __dmul_rn(0.5, sx[2][1]));
+      cx0[2] = shrink_to(sx[0][0], sx[1][0]); cx1[2] = shrink_to(sx[0][1], sx[1][1]);
+      cx0[3] = shrink_to(sx[0][0], sx[2][0]); cx1[3] = shrink_to(sx[0][1], sx[2][1]);
+      const int jl = lane & 3;
+      const double t0 = (jl == 0) ? cx0[0] : (jl == 1) ? cx0[1] : (jl == 2) ? cx0[2] : cx0[3];
+      const double t1 = (jl == 0) ? cx1[0] : (jl == 1) ? cx1[1] : (jl == 2) ? cx1[2] : cx1[3];
+      cmask = __ballot_sync(FULL, gp_head(t0, t1, jit10, P.r2_10, m).fail01) & 0xFu;
+    }
   }
   NMOut o;
   o.x0 = sx[0][0];
@@ -706,6 +744,7 @@ struct FitArgs {
   unsigned int* queue;    // next task to hand out; zero on entry
   const int* order;       // optional [ntasks]: queue position -> task (longest searches first)
   int d, m, R, ntasks;
+  int head_batch;         // 1: pre-decide the four points of an all-inf Nelder-Mead iteration at once (0: tests)
   int j0, dl;             // output dimensions [j0, j0+dl) handled by this launch (a rank's share; dl = d: all)
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
@@ -760,7 +799,7 @@ gp_fit_predict_kernel(FitArgs A) {
     const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
     const signed char* st = A.starts + gtask * 2;
     const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol, P, y, m,
-                                   lane, Lt, hml);
+                                   lane, Lt, hml, A.head_batch != 0);
     unsigned int prior = 0;
     if (lane == 0) {
       A.res[(long long)task * 3] = o.f;
@@ -1053,7 +1092,8 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.order = order;
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
-  A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
+  A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
+  A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
   int rc = 0;
   DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   return rc;

@@ -399,6 +399,39 @@ def test_fit_predict_vs_oracle(handle, n, d, m, R):
     assert np.all(det['fval_opt'][0] <= odet['fval_opt'] + 0.2 * np.abs(odet['fval_opt']))
 
 
+def test_all_inf_searches_steady_state_neighbours(handle):
+    """identical neighbour rows (the FHN target reaches a steady state): the kernel matrix is exactly singular
+    for amplitudes above jitter / 4 ulp, every vertex of such a search is +inf, SciPy's fatol test sees
+    |inf - inf| = NaN and the search runs all maxfev = 400 evaluations and returns its start point.  The device
+    pre-decides the four points of such an iteration at once (gp_head in four lanes): results must be the bits
+    of the one-by-one evaluation (NNGP_FIT_NO_HEAD_BATCH) and show the 400-evaluation pattern."""
+    import os
+    rng = np.random.default_rng(5)
+    n, d, m = 64, 6, 20
+    x = np.tile(rng.uniform(-1, 1, (1, d)), (n, 1))
+    x[:8] += 1e-3 * rng.standard_normal((8, d))       # a few distinct rows far away
+    y = 1e-4 * rng.standard_normal((n, d))
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    q = x[20:21] + 0.0
+    starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+    got = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+    try:
+        os.environ["NNGP_FIT_NO_HEAD_BATCH"] = "1"
+        ref = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+    finally:
+        del os.environ["NNGP_FIT_NO_HEAD_BATCH"]
+    for key in ("nfev", "thetas", "fvals", "theta_opt", "fval_opt", "jitter_opt"):
+        assert np.array_equal(got[key], ref[key], equal_nan=True), key
+    assert np.array_equal(got["pred"], ref["pred"], equal_nan=True)
+    inf_runs = np.isinf(got["fvals"][0])
+    assert inf_runs.sum() >= 5, "the case must contain searches that see +inf everywhere"
+    assert np.all(got["nfev"][0][inf_runs] == 400)
+    assert np.array_equal(got["thetas"][0][inf_runs], starts[0][inf_runs].astype(float))
+    assert np.all(got["nfev"][0][~inf_runs] < 400)
+
+
 def test_predict_is_repeatable_after_other_workspace_users(handle):
     """the fit kernel leaves its completion counters zero for the next launch; anything else that uses the
     handle's workspace in between (micro-benchmarks, a large kNN) must not leave them dirty"""
