@@ -83,7 +83,9 @@ class CudaSolverRK(SolverAbstr):
         h, sys = self.device()
         t0 = np.asarray(t0, dtype=float).ravel()
         t1 = np.asarray(t1, dtype=float).ravel()
-        u0 = np.asarray(u0, dtype=float).reshape(t0.shape[0], -1)
+        u0 = np.asarray(u0, dtype=float).reshape(t0.shape[0], self.ode.get_dim())
+        if t0.shape[0] == 0:
+            return u0.copy()  # no slices left (all converged): nothing to launch
         steps = int(steps)
         if steps > self.thresh:
             # solver.py:89-96 (paging quirk kept: every page integrates with the TOTAL step count)

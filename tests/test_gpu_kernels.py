@@ -488,3 +488,41 @@ def test_predict_on_reference_run_samples(handle, name):
             same_pred += bool(abs(out["pred"][0, j] - s["preds"][j]) <= 1e-8 * abs(s["preds"][j]) + 1e-13)
     assert as_good >= 0.9 * total, (as_good, total)
     print(f"{name}: optimum as good as the reference's in {as_good}/{total}, identical prediction in {same_pred}/{total}")
+
+
+def test_empty_and_extreme_inputs(handle):
+    """edge cases through the C ABI: zero slices / rows / queries are no-ops, m = 1 and m = 32 (the lane limit)
+    work, a dataset shorter than m is an error (the reference would silently use fewer neighbours only in
+    'adaptive' mode, which the host mirror clamps before calling), d = 1"""
+    rng = np.random.default_rng(9)
+    ode = nn.Lorenz(normalization='-11')
+    s = nn.CudaSolverRK(ode.get_vector_field(), Ng=3, Nf=5, F='RK4', G='RK1')
+    assert s.run_F_batch(np.zeros(0), np.zeros(0), np.zeros((0, 3))).shape == (0, 3)
+    n, d = 50, 1
+    x = rng.uniform(-1, 1, (n, d))
+    y = 1e-3 * np.sin(3 * x)
+    handle.dataset_reset()
+    handle.dataset_reserve(64, d)
+    handle.dataset_append_host(x[:0], y[:0])          # zero rows
+    assert handle.dataset_rows() == 0
+    handle.dataset_append_host(x, y)
+    idx, dist = handle.knn_host(np.zeros((0, d)), 5)  # zero queries
+    assert idx.shape == (0, 5)
+    q = np.array([[0.123]])
+    for m in (1, 2, 32):
+        starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+        out = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+        oi, okq = onn.knn(q[0], x, m)
+        assert np.array_equal(out["idx"][0], oi)
+        r2 = onn.pairwise_sqdist(x[oi], x[oi])
+        want = onn.posterior_mean(r2, okq, y[oi, 0], out["theta_opt"][0, 0], out["jitter_opt"][0, 0])
+        K = onn.se_kernel_from_r2(r2, out["theta_opt"][0, 0]) + np.eye(m) * 10 ** out["jitter_opt"][0, 0]
+        cond = np.linalg.cond(K)
+        assert np.isfinite(out["pred"][0, 0]), m
+        if np.isfinite(want) and cond < 1e12:  # beyond, LAPACK and the device may disagree on whether K factorises
+            assert abs(out["pred"][0, 0] - want) <= max(1e-8, 4 * cond * 2.2e-16) * abs(want) + 1e-14, (m, cond)
+        assert np.all(out["nfev"] >= 3) and np.all(out["nfev"] <= 400)
+    with pytest.raises(_lib.NNGPError, match="fewer than m"):
+        handle.knn_host(q, 32, n_rows=20)
+    with pytest.raises(_lib.NNGPError, match="outside"):
+        handle.predict_host(q, 33, rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8), 1, 0.1, 0.1)
