@@ -340,7 +340,7 @@ def run_e2e(args, nn, ode, solver, cfg, h, dev, world, rank, sync_all, dist):
 
     def iteration():
         nonlocal h2d, d2h
-        model = nn.CudaNNGP(n=d, N=N, nn=m, seed=45, handle=h)
+        model = nn.CudaNNGP(n=d, N=N, nn=m, seed=45, handle=h, shard_predict=(world > 1))
         res = list(pool.map(solver.run_F_timed, t[0:N], t[1:N + 1], [u_cur[i] for i in range(N)]))
         uF = np.empty((N + 1, d))
         uF[0] = u_cur[0]

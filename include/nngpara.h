@@ -119,6 +119,12 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
                       int n_restarts, const signed char* starts, double fatol, double xatol,
                       double* pred, long long* idx, double* theta_opt, double* jitter_opt,
                       double* fval_opt, int* nfev, double* fvals, double* thetas);
+/* One rank's share of a predict: the same, fits only for the output dimensions [j0, j0+dl) of a single query
+ * (dl < 0: all); pred / theta_opt / ... are written for those dimensions only.                          */
+int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
+                            int n_restarts, const signed char* starts, double fatol, double xatol, int j0, int dl,
+                            double* pred, long long* idx, double* theta_opt, double* jitter_opt,
+                            double* fval_opt, int* nfev, double* fvals, double* thetas);
 /* objective only: nll[nq,d,nt] at theta[nq,d,nt,2], jitter10[nq,d,nt] (= 10**jitter), the
  * `log_lik` of models.py:240-252 (+inf where the reference returns inf). */
 int nngp_gp_nll(nngp_handle_t h, const long long* d_idx, int nq, int m, int nt,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "nngp_knn_host": (ci, [vp, vp, ci, ci, cll, vp, vp]),
     "nngp_fit_predict": (ci, [vp, vp, vp, vp, ci, ci, ci, vp, cd, cd, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nngp_predict_host": (ci, [vp, vp, ci, ci, cll, ci, vp, cd, cd, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nngp_predict_host_block": (ci, [vp, vp, ci, ci, cll, ci, vp, cd, cd, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nngp_gp_nll": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp]),
     "nngp_gp_mean": (ci, [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]),
     "nngp_sweep": (ci, [vp, ci, ci, ci, cll, vp, ci, ci, ci, ci, vp, cd, cd, vp, vp, ci, vp]),
@@ -204,7 +205,7 @@ class Handle:
     def knn(self, d_q, nq, m, n_rows, d_idx, d_dist, stream=None):
         self.check(self.lib.nngp_knn(self.h, _ptr(d_q), int(nq), int(m), int(n_rows), _ptr(d_idx), _ptr(d_dist), stream))
 
-    def predict_host(self, q, m, starts, n_restarts, fatol, xatol, n_rows=0, details=False):
+    def predict_host(self, q, m, starts, n_restarts, fatol, xatol, n_rows=0, details=False, block=None):
         q = as_f64(q)
         q = q.reshape(-1, q.shape[-1])
         nq, d = q.shape
@@ -222,9 +223,11 @@ class Handle:
             fvals = np.empty((nq, d, 9, n_restarts))
             thetas = np.empty((nq, d, 9, n_restarts, 2))
             out.update(idx=idx, theta_opt=th, jitter_opt=jit, fval_opt=fv, nfev=nfev, fvals=fvals, thetas=thetas)
-        self.check(self.lib.nngp_predict_host(self.h, _ptr(q), nq, int(m), int(n_rows), int(n_restarts),
-                                              _ptr(starts), float(fatol), float(xatol), _ptr(pred), _ptr(idx),
-                                              _ptr(th), _ptr(jit), _ptr(fv), _ptr(nfev), _ptr(fvals), _ptr(thetas)))
+        j0, dl = block if block is not None else (0, -1)  # block: (first dim, count) -- only those dims are fitted
+        self.check(self.lib.nngp_predict_host_block(self.h, _ptr(q), nq, int(m), int(n_rows), int(n_restarts),
+                                                    _ptr(starts), float(fatol), float(xatol), int(j0), int(dl),
+                                                    _ptr(pred), _ptr(idx), _ptr(th), _ptr(jit), _ptr(fv), _ptr(nfev),
+                                                    _ptr(fvals), _ptr(thetas)))
         return out
 
     def fit_predict(self, d_q, d_idx, d_dist, nq, m, n_restarts, d_starts, fatol, xatol, d_pred,

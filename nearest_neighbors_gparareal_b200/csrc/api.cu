@@ -489,9 +489,23 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
                       int n_restarts, const signed char* starts, double fatol, double xatol,
                       double* pred, long long* idx, double* theta_opt, double* jitter_opt,
                       double* fval_opt, int* nfev, double* fvals, double* thetas) {
+  return nngp_predict_host_block(h, q, nq, m, n_rows, n_restarts, starts, fatol, xatol, 0, -1, pred, idx, theta_opt,
+                                 jitter_opt, fval_opt, nfev, fvals, thetas);
+}
+
+int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
+                            int n_restarts, const signed char* starts, double fatol, double xatol, int j0, int dl,
+                            double* pred, long long* idx, double* theta_opt, double* jitter_opt,
+                            double* fval_opt, int* nfev, double* fvals, double* thetas) {
   if (nq <= 0) return 0;
   if (!h->ds_x) return nngp_fail(h, "predict: dataset is empty");
   const int d = h->ds_d, R = n_restarts;
+  if (dl < 0) {
+    j0 = 0;
+    dl = d;
+  }
+  if (j0 < 0 || dl < 1 || j0 + dl > d) return nngp_fail(h, "predict: dimension block [%d,%d) outside [0,%d)", j0, j0 + dl, d);
+  if (dl != d && nq != 1) return nngp_fail(h, "predict: a dimension block needs a single query (got %d)", nq);
   const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
   const size_t nqd = (size_t)nq * d, ntask = nqd * NNGP_N_JITTER * R;
   size_t total = 0;
@@ -517,7 +531,11 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
   if (int rc = ensure_done_zero(h, fws, nq, d, m, R, st)) return rc;
   if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
   if (int rc = gp_prep_launch(h, gidx, nq, m, (double*)fws, st)) return rc;
-  if (int rc = gp_order_launch(h, gst, nq, d * NNGP_N_JITTER * R, 1, order, st)) return rc;
+  if (dl == d) {
+    if (int rc = gp_order_launch(h, gst, nq, d * NNGP_N_JITTER * R, 1, order, st)) return rc;
+  } else {  // the searches of the block are a contiguous range of the (single) query's task list
+    if (int rc = gp_order_launch(h, gst + (size_t)j0 * NNGP_N_JITTER * R * 2, 1, dl * NNGP_N_JITTER * R, 0, order, st)) return rc;
+  }
   if (int rc = gp_fit_predict_launch(h, gidx, gdist, fws, next_queue(h, st), order, nq, m, R, gst, fatol, xatol,
                                      (double*)(dev + o_pred), nullptr, d,
                                      theta_opt ? (double*)(dev + o_th) : nullptr,
@@ -525,7 +543,7 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
                                      fval_opt ? (double*)(dev + o_fv) : nullptr,
                                      nfev ? (int*)(dev + o_nfev) : nullptr,
                                      fvals ? (double*)(dev + o_fvals) : nullptr,
-                                     thetas ? (double*)(dev + o_thetas) : nullptr, st))
+                                     thetas ? (double*)(dev + o_thetas) : nullptr, st, j0, dl))
     return rc;
   NNGP_CUDA(h, cudaMemcpyAsync(pred, dev + o_pred, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));
   if (idx) NNGP_CUDA(h, cudaMemcpyAsync(idx, gidx, sizeof(long long) * nq * m, cudaMemcpyDeviceToHost, st));

@@ -508,7 +508,7 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
 //          per SM (a rank of a multi-GPU run), where a slice's own step time is what counts.
 // ---------------------------------------------------------------------------------------
 template <int TY, int TB>
-struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) : ((TB <= 128) ? 4 : 1); };
+struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) : ((TB <= 128) ? 2 : 1); };
 
 template <int S, int TY, int TB>
 __global__ void __launch_bounds__(TB, TileOcc<TY, TB>::value)

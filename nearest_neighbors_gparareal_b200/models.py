@@ -14,6 +14,7 @@ import time
 import numpy as np
 
 from . import _lib
+from .utils import dim_block
 
 N_JITTER = 9  # models.py:186  jitter = np.arange(-20, -11)
 
@@ -99,6 +100,10 @@ class CudaNNGP(ModelAbstr):
         self.calc_detail_avg = kwargs.get('calc_detail_avg', False)
         self.calc_parall_overhead = kwargs.get('calc_parall_overhead', False)
         self.collect_nfev = kwargs.get('collect_nfev', False)
+        # W > 1 torch.distributed ranks calling predict in lockstep (the host loop under torchrun): each rank fits
+        # d/W of the output dimensions and the predictions are all-gathered (needs d % W == 0)
+        self.shard_predict = kwargs.get('shard_predict', False)
+        self.group = kwargs.get('group', None)
         if self.calc_detail_avg:
             self.detail_avg = np.zeros((N, N))
         if self.calc_parall_overhead:
@@ -151,8 +156,11 @@ class CudaNNGP(ModelAbstr):
         new_x = np.asarray(new_x, dtype=float).reshape(1, -1)
         starts = self.draw_starts(1)
         s = time.time()
+        block = self._block()
         out = h.predict_host(new_x, m, starts, self.n_restarts, self.fatol, self.xatol,
-                             details=details or self.collect_nfev)
+                             details=details or self.collect_nfev, block=block)
+        if block is not None:
+            out['pred'] = self._gather(out['pred'], block)
         el = time.time() - s
         n_tasks = self.n * N_JITTER * self.n_restarts
         self.tot_train_t += el
@@ -166,6 +174,28 @@ class CudaNNGP(ModelAbstr):
             self.overhead[self.k, i] = 0.0
         preds = out['pred'][0]
         return (preds, out) if details else preds
+
+    def _block(self):
+        if not self.shard_predict:
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world = dist.get_world_size(self.group)
+        if world == 1 or self.n % world != 0:
+            return None
+        return dim_block(self.n, dist.get_rank(self.group), world)
+
+    def _gather(self, pred, block):
+        """all-gather of the ranks' prediction blocks (d/W doubles each); details stay per-rank"""
+        import torch
+        import torch.distributed as dist
+        j0, dl = block
+        dev = 'cuda' if dist.get_backend(self.group) == 'nccl' else 'cpu'
+        t = torch.from_numpy(np.ascontiguousarray(pred[0])).to(dev)
+        mine = t[j0:j0 + dl] if dev == 'cuda' else t[j0:j0 + dl].clone()
+        dist.all_gather_into_tensor(t, mine, group=self.group)
+        return t.cpu().numpy()[None, :]
 
     def get_times(self):
         out = super().get_times()

@@ -19,6 +19,7 @@ from .models import BareParareal, CudaNNGP, ModelAbstr, N_JITTER
 from .pool import CudaPool, MyPool
 from .solver import CudaSolverRK, SolverAbstr
 from .systems import ODE
+from .utils import dim_block
 
 
 def slice_block(I, N, rank, world):
@@ -28,13 +29,6 @@ def slice_block(I, N, rank, world):
     lo = min(I + rank * chunk, N)
     cnt = max(0, min(chunk, N - lo))
     return chunk, lo, cnt
-
-
-def dim_block(d, rank, world):
-    """Output dimensions [j0, j0+dl) whose fits `rank` runs when the sweep is sharded by dimension
-    (equal blocks: d must be a multiple of world)."""
-    dl = d // world
-    return rank * dl, dl
 
 
 def gather_fine_rows(uF, I, chunk, rank, world, group=None):

@@ -25,3 +25,10 @@ class Normalize():
         if self.norm_type == '-11':
             return 2 / (self.mx - self.mn)
         return 1
+
+
+def dim_block(d, rank, world):
+    """Output dimensions [j0, j0+dl) whose fits `rank` runs when a predict is sharded by dimension over
+    `world` ranks (equal blocks: d must be a multiple of world)."""
+    dl = d // world
+    return rank * dl, dl

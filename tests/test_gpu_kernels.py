@@ -526,3 +526,29 @@ def test_empty_and_extreme_inputs(handle):
         handle.knn_host(q, 32, n_rows=20)
     with pytest.raises(_lib.NNGPError, match="outside"):
         handle.predict_host(q, 33, rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8), 1, 0.1, 0.1)
+
+
+def test_predict_dimension_blocks_equal_full_predict(handle):
+    """nngp_predict_host_block: the fits of a predict split by output dimension (a rank's share) give, block by
+    block, the bits of the full predict -- predictions and per-search details"""
+    rng = np.random.default_rng(21)
+    n, d, m = 700, 24, 14
+    x, y = make_dataset(rng, n, d)
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    q = x[11:12] + 1e-3
+    starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+    full = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+    for world in (2, 3, 8):
+        dl = d // world
+        for rank in range(world):
+            j0 = rank * dl
+            part = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True, block=(j0, dl))
+            assert np.array_equal(part["idx"], full["idx"])
+            for key in ("pred", "theta_opt", "jitter_opt", "fval_opt", "nfev", "fvals", "thetas"):
+                assert np.array_equal(part[key][0, j0:j0 + dl], full[key][0, j0:j0 + dl]), (key, world, rank)
+    with pytest.raises(_lib.NNGPError, match="outside"):
+        handle.predict_host(q, m, starts, 1, 0.1, 0.1, block=(20, 8))
+    with pytest.raises(_lib.NNGPError, match="single query"):
+        handle.predict_host(np.concatenate([q, q]), m, np.concatenate([starts, starts]), 1, 0.1, 0.1, block=(0, 8))
