@@ -1,5 +1,5 @@
 """Aggregate an ncu launch list (--metrics gpu__time_duration.sum --csv) of `bench.py --steps 1 --warmup 1` into the
-per-kernel shares of the timed step: the step starts at the LAST fine-propagator launch (grid = all slices).
+per-kernel shares of the timed step: the step starts at the first launch of the LAST run of fine-propagator launches.
 usage: python scripts/ncu_step_summary.py launches.csv out.csv"""
 import csv, sys, collections
 rows = []
@@ -14,6 +14,8 @@ for r in rd:
         rows.append((int(r["ID"]), r["Kernel Name"], r["Grid Size"], r["Block Size"], v))
 fine = [i for i, r in enumerate(rows) if "rk_fhn_tile_kernel<11" in r[1] or ("rk_pde_kernel<FhnPde, 11" in r[1])]
 start = fine[-1]
+while start - 1 in fine:  # the fine step is a run of consecutive chunk launches
+    start -= 1
 step = rows[start:]
 agg = collections.OrderedDict()
 for _, name, grid, block, us in step:
