@@ -7,23 +7,26 @@
 // posterior mean (models.py:162-168) -- one launch per predict instead of d*9*R pickled
 // tasks through pool.map.
 //
-// Mapping.  One WARP per Nelder-Mead search.  The searches of a launch (nq*d*9*R tasks) sit in
-// a queue; a persistent grid of independent warps pulls them with an atomic counter, so a warp
-// that finishes a short search immediately starts another one (search lengths vary from ~10 to
-// 400 objective evaluations).  The warp that completes the last search of an (query, dimension)
-// pair applies the selection rule and computes the posterior mean (no block barrier, no second
-// launch).  Inside a warp lane r owns row r of the m x m kernel matrix (m <= 32) in registers:
-// right-looking Cholesky, pivot broadcast by shuffle, column broadcast through a per-warp
-// shared-memory tile read with warp-uniform 16-byte loads, forward solve fused into the
-// factorisation.  The m x m squared-distance matrix of the neighbours is computed once per query
-// (gp_prep_kernel) and read through L1 by all d*9*R searches.
+// Mapping.  One WARP per Nelder-Mead search.  The searches of a launch (nq*d*9*R tasks, or one rank's
+// block of output dimensions) sit in a queue ordered by gp_order_kernel; a persistent grid of
+// independent warps pulls them with an atomic counter, so a warp that finishes a short search
+// immediately starts another one (search lengths vary from ~10 to 400 objective evaluations).  The
+// warp that completes the last search of an (query, dimension) pair applies the selection rule and
+// computes the posterior mean (no block barrier, no second launch).  Inside a warp the M(M-1)/2
+// kernel entries are spread over the lanes, exchanged through a per-warp shared-memory tile, and
+// lane r owns row r of the m x m kernel matrix (m <= 32) in registers: square-root-free
+// right-looking LDL^T, pivot broadcast by shuffle, column broadcast through the tile with
+// warp-uniform 16-byte loads, forward solve fused into the factorisation (gp_core).  The m x m
+// squared-distance matrix of the neighbours is computed once per query (gp_prep_kernel); a lane keeps
+// the distances of its entries in registers for the whole search.
 //
 // Arithmetic.  The simplex arithmetic uses explicitly rounded (non-fused) operations in SciPy's
-// order.  The objective is the reference's  0.5 y^T K^-1 y + sum log L_ii + (m/2) log 2 pi  with the
-// data-fit term evaluated as |L^-1 y|^2 (identical in exact arithmetic; the reference's own
-// optimiser trajectories are not reproducible below 1 ulp of the objective, see DESIGN.md
-// "ties"), pivots from rsqrt.  A pivot <= 0 or NaN fails like LAPACK potf2 and makes the
-// objective +inf exactly as the reference does (NaN -> inf, models.py:250-251).
+// order.  The objective is the reference's  0.5 y^T K^-1 y + sum log L_ii + (m/2) log 2 pi  evaluated
+// as 0.5 (sum_k z_k^2 / d_k + log prod_k d_k) with the LDL^T pivots d_k = L_kk^2 and z = L'^-1 y
+// (identical in exact arithmetic; the reference's own optimiser trajectories are not reproducible
+// below 1 ulp of the objective, see DESIGN.md "ties").  A pivot that is <= 4 ulp of the diagonal,
+// <= 0 or NaN fails like LAPACK potf2 and makes the objective +inf exactly as the reference does
+// (NaN -> inf, models.py:250-251).
 #include "common.cuh"
 
 #include <cmath>
@@ -75,7 +78,7 @@ __constant__ double c_exp[12] = {
     -1.1451100898021838e-10,      // [7] -log10(2) lo
     2.302585092994046,            // [8] ln(10) hi
     -2.1707562233822494e-16,      // [9] ln(10) lo
-    0.375, 0.5};                  // [10], [11] rsqrt correction
+    0.0, 0.0};                    // [10], [11] unused
 __constant__ double c_log[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                 1.479819860511658591e-01,
@@ -162,16 +165,6 @@ __device__ __forceinline__ void exp10_pair(double x0, double x1, double& o0, dou
   exp_reduced_vec<2>(y, k, o);
   o0 = o[0];
   o1 = o[1];
-}
-
-__device__ __forceinline__ double rsqrt_pos(double p) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-  const double t = y * y;
-  const double e = fma(-p, t, 1.0);
-  const double c = fma(e, c_exp[10], c_exp[11]);
-  const double ye = y * e;
-  return fma(c, ye, y);
 }
 
 // 1/p for p > 0: seed relative error e0 ~ 2^-20; y (1 + e + e^2) has error e0^3
@@ -420,26 +413,18 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   // one batch.  Every lane sees every pivot d_k and (L'^-1 y)_k, so  y^T K^-1 y = sum w_k^2 / d_k  and
   // log det K = log prod d_k (mantissa product + exponent sum) are accumulated redundantly in all
   // lanes: no warp reduction, one logarithm.
-#ifdef FIT_NO_PREFETCH
-  constexpr bool PREFETCH = false;  // experiment: fewer registers (more warps per SM), column read where used
-#else
-  constexpr bool PREFETCH = true;
-#endif
-  constexpr int PREFETCH_M = PREFETCH ? M : 2;
-  auto load_col = [&](int k, double (&u)[PREFETCH_M]) {
+  auto load_col = [&](int k, double (&u)[M]) {
     // u[j] = column k entry of row j (unscaled), j > k; uniform addresses -> broadcast loads
-    if constexpr (PREFETCH) {
-      int j = k + 1;
-      if (j < M && (j & 1)) {
-        u[j] = Kt[k * LD + j];
-        j++;
-      }
+    int j = k + 1;
+    if (j < M && (j & 1)) {
+      u[j] = Kt[k * LD + j];
+      j++;
+    }
 #pragma unroll
-      for (; j + 1 < M; j += 2) {
-        const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
-        u[j] = u2.x;
-        u[j + 1] = u2.y;
-      }
+    for (; j + 1 < M; j += 2) {
+      const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
+      u[j] = u2.x;
+      u[j + 1] = u2.y;
     }
   };
   double dd = dd0;
@@ -447,11 +432,11 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   double quad = 0.0, prod0 = 1.0, prod1 = 1.0;
   double inv_own = 1.0, w_own = 0.0;  // ALPHA: 1/d_r and (L'^-1 y)_r of the own row
   bool ok = true;
-  double u[PREFETCH_M];
+  double u[M];
   double p = shfl(dd, 0), zk = shfl(z, 0);
   if (lane > 0 && lane < M) Kt[lane] = a[0];
   __syncwarp();
-  if constexpr (PREFETCH) load_col(0, u);
+  load_col(0, u);
 #pragma unroll
   for (int k = 0; k < M; k++) {
     ok = ok && (p > pmin);  // failed factorisation (potf2: pivot <= 0 or NaN) -> +inf
@@ -460,11 +445,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     // (at the FHN target 14 % of the searches, 57 % of the evaluations, and the serial chain that ends
     // the launch).  Near-duplicate neighbours fail at the first pivots: leave early at a few fixed
     // steps (warp-uniform vote, so the shuffles below stay convergent).
-#ifndef FIT_DENSE_CHECKS
     if (!ALPHA && (k == 1 || k == 2 || k == 4 || k == 8 || k == 14) && k < M - 1) {
-#else
-    if (!ALPHA && (k <= 6 || k == 8 || k == 11 || k == 14) && k >= 1 && k < M - 1) {
-#endif
       if (__any_sync(FULL, !ok)) {
         GpOut bad;
         bad.amp = amp;
@@ -485,31 +466,16 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     dd = fma(-w, a[k], dd);
     z = fma(-w, zk, z);
     if (k + 1 < M) {
-      a[k + 1] = fma(-w, PREFETCH ? u[(PREFETCH ? k + 1 : 0)] : Kt[k * LD + k + 1], a[k + 1]);
+      a[k + 1] = fma(-w, u[k + 1], a[k + 1]);
       p = shfl(dd, k + 1);
       zk = shfl(z, k + 1);
       if (k + 2 < M) {
         if (lane > k + 1 && lane < M) Kt[(k + 1) * LD + lane] = a[k + 1];
         __syncwarp();
       }
-      if constexpr (PREFETCH) {
 #pragma unroll
-        for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
-        if (k + 2 < M) load_col(k + 1, u);
-      } else {
-        // column k was stored before the previous __syncwarp pair; rows differ per step, no hazard
-        int j = k + 2;
-        if (j < M && (j & 1)) {
-          a[j] = fma(-w, Kt[k * LD + j], a[j]);
-          j++;
-        }
-#pragma unroll
-        for (; j + 1 < M; j += 2) {
-          const double2 u2 = *reinterpret_cast<const double2*>(&Kt[k * LD + j]);
-          a[j] = fma(-w, u2.x, a[j]);
-          a[j + 1] = fma(-w, u2.y, a[j + 1]);
-        }
-      }
+      for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
+      if (k + 2 < M) load_col(k + 1, u);
     }
     if (!ALPHA) {  // off the critical path; a padding row has z = 0 and is left out of the determinant
       quad = fma(zkk * zkk, ip, quad);
