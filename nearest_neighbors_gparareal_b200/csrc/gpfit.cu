@@ -477,10 +477,16 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       for (int j = k + 2; j < M; j++) a[j] = fma(-w, u[j], a[j]);
       if (k + 2 < M) load_col(k + 1, u);
     }
-    if (!ALPHA) {  // off the critical path; a padding row has z = 0 and is left out of the determinant
+    if (!ALPHA) {  // off the critical path; a padding row has z = 0 and contributes nothing to the sum
       quad = fma(zkk * zkk, ip, quad);
-      const double pe = (k < m) ? pk : 1.0;
-      if (k < M / 2) prod0 = prod0 * pe; else prod1 = prod1 * pe;
+      if (k < M / 2) prod0 = prod0 * pk; else prod1 = prod1 * pk;
+    }
+  }
+  // a padding row (m odd: one) keeps the untouched diagonal dd0 as its pivot: take it out of the determinant
+  if (!ALPHA && m < M) {
+    const double id0 = rcp_pos(dd0);
+    for (int r = m; r < M; r++) {
+      if (r < M / 2) prod0 = prod0 * id0; else prod1 = prod1 * id0;
     }
   }
   GpOut o;
