@@ -551,6 +551,13 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
     const double h = step_size(h_mode, t0, t1, step, n, steps);
     double hv[3];
     FhnPde::step_coeffs(A, h, hv);
+    // xn: the next stage's input without its newest term, u + sum_{j<i} a_{i+1,j} k_j -- formed while the
+    // neighbour loads of stage i are in flight (same ascending order of the terms: same bits)
+    double xn[2][NV];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int q = 0; q < NV; q++) xn[c][q] = u[c][q];
 #pragma unroll
     for (int i = 0; i < S; i++) {
       double* buf = sm + par * (2 * npts);
@@ -560,10 +567,8 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
       for (int c = 0; c < 2; c++) {
 #pragma unroll
         for (int q = 0; q < NV; q++) {
-          double x = u[c][q];
-#pragma unroll
-          for (int j = 0; j < i; j++)
-            if (a_nonzero<S>(i, j)) x = fma(T.a[i * NNGP_MAX_STAGES + j], k[c][q][j], x);
+          double x = xn[c][q];
+          if (i > 0 && a_nonzero<S>(i, i - 1)) x = fma(T.a[i * NNGP_MAX_STAGES + i - 1], k[c][q][i - 1], x);
           w[c][q] = x;
         }
         if (active) {
@@ -573,16 +578,39 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
         }
       }
       __syncthreads();
+      double2 up[2], dn[2];
+      double lf[2][TY], rt[2][TY];
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         const double* b = buf + c * npts;
-        const double2 up = *reinterpret_cast<const double2*>(b + oup);
-        const double2 dn = *reinterpret_cast<const double2*>(b + odn);
+        up[c] = *reinterpret_cast<const double2*>(b + oup);
+        dn[c] = *reinterpret_cast<const double2*>(b + odn);
 #pragma unroll
         for (int r = 0; r < TY; r++) {
-          const double l = b[ol0 + r * dx], rr = b[or0 + r * dx];
-          const double ax = (r == 0) ? up.x : w[c][2 * (r - 1)], ay = (r == 0) ? up.y : w[c][2 * (r - 1) + 1];
-          const double bx = (r == TY - 1) ? dn.x : w[c][2 * (r + 1)], by = (r == TY - 1) ? dn.y : w[c][2 * (r + 1) + 1];
+          lf[c][r] = b[ol0 + r * dx];
+          rt[c][r] = b[or0 + r * dx];
+        }
+      }
+      if (i + 1 < S) {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int q = 0; q < NV; q++) {
+            double x = u[c][q];
+#pragma unroll
+            for (int j = 0; j < i; j++)
+              if (a_nonzero<S>(i + 1, j)) x = fma(T.a[(i + 1) * NNGP_MAX_STAGES + j], k[c][q][j], x);
+            xn[c][q] = x;
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const double2 up_c = up[c], dn_c = dn[c];
+#pragma unroll
+        for (int r = 0; r < TY; r++) {
+          const double l = lf[c][r], rr = rt[c][r];
+          const double ax = (r == 0) ? up_c.x : w[c][2 * (r - 1)], ay = (r == 0) ? up_c.y : w[c][2 * (r - 1) + 1];
+          const double bx = (r == TY - 1) ? dn_c.x : w[c][2 * (r + 1)], by = (r == TY - 1) ? dn_c.y : w[c][2 * (r + 1) + 1];
           // (v[iy-1] + v[ix-1]) + (v[ix+1] + v[iy+1]) as in FhnPde::eval_k
           sn[c][2 * r] = (ax + l) + (w[c][2 * r + 1] + bx);
           sn[c][2 * r + 1] = (ay + w[c][2 * r]) + (rr + by);
