@@ -193,6 +193,45 @@ def test_time_slice_sharding_all_gather_gloo_world2(tmp_path):
     assert codes == [0, 0]
 
 
+_WORKER_DIM = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from nearest_neighbors_gparareal_b200.models import CudaNNGP
+from nearest_neighbors_gparareal_b200.utils import dim_block
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[4])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+ok = True
+for d in (8, 6):
+    model = CudaNNGP(n=d, N=4, nn=5, shard_predict=True)   # no device call is made in this test
+    blk = model._block()
+    ok &= blk == dim_block(d, rank, world)
+    j0, dl = blk
+    pred = np.full((1, d), np.nan)
+    pred[0, j0:j0 + dl] = np.arange(j0, j0 + dl) * 1.5 + 7      # this rank's share of the fits
+    full = model._gather(pred, blk)
+    ok &= bool(np.array_equal(full, (np.arange(d) * 1.5 + 7)[None, :]))
+model = CudaNNGP(n=7, N=4, nn=5, shard_predict=True)     # 7 % 2 != 0: not sharded
+ok &= model._block() is None
+ok &= CudaNNGP(n=8, N=4, nn=5)._block() is None           # sharding is opt-in
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+def test_dimension_sharded_predict_all_gather_gloo_world2(tmp_path):
+    """N>1 host path on CPU: each rank holds the predictions of its block of output dimensions, one all-gather of
+    d/W doubles, the full prediction everywhere (CudaNNGP._block / _gather)"""
+    script = tmp_path / "worker_dim.py"
+    script.write_text(_WORKER_DIM)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port]) for r in range(2)]
+    codes = [p.wait(timeout=180) for p in procs]
+    assert codes == [0, 0]
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference's CPU path = the oracle port on the host cores) prints ONE JSON
     line with the contract keys; small workload so that it runs in seconds on CPU.  Under torchrun only rank 0
