@@ -54,6 +54,10 @@ class ModelAbstr():
     def predict(self, new_x, prev_F, prev_G):
         raise Exception('Not implemented')
 
+    def restore_attrs(self, pool):
+        """re-attach what store() stripped (models.py:262-270); nothing to do for models without a pool"""
+        pass
+
     def store(self):
         saved = {k: self.__dict__.get(k) for k in ('pool', '_handle') if k in self.__dict__}
         for k in saved:

@@ -10,6 +10,8 @@ fine solves (sharded by time slice across ranks, exchanged with a single all-gat
 dataset append, the fused on-device sweep (nngp_sweep) and one small device->host read of the
 per-slice errors per iteration.
 """
+import os
+import pickle
 import time
 
 import numpy as np
@@ -71,15 +73,76 @@ class Parareal():
             pool = CudaPool()
         return pool
 
-    def run(self, *args, **kwargs):
+    def run(self, *args, _run_from_int=False, **kwargs):
         pool = self._get_pool(*args, **kwargs)
         kwargs['pool'] = pool
         try:
-            out = self._run(*args, **kwargs)
+            if _run_from_int:
+                out = self._run_from_int(*args, **kwargs)
+            else:
+                out = self._run(*args, **kwargs)
         except Exception:
             pool.shutdown()
             raise
         pool.shutdown()
+        return out
+
+    # ---- intermediate checkpoints (parareal.py:114-209, 420-431) -------------------------------
+    def store(self, name, path='', mdl=None, objs=None):
+        """Pickles the driver without its ODE / solver (device handles do not pickle), with the model copy
+        `mdl.store()` and the loop state `objs` -- parareal.py:114-139."""
+        if len(path) > 0 and not os.path.exists(path):
+            os.makedirs(path)
+        ode, solver, f = self.ode, self.solver, self.f
+        self.ode = self.solver = self.f = None
+        pool = None
+        if objs is not None:
+            pool = objs['kwargs'].get('pool', None)
+            objs['kwargs']['pool'] = None
+            self.objs = objs
+        if mdl is not None:
+            self.mdl = mdl.store()
+        try:
+            with open(os.path.join(path, name), 'wb') as _file:
+                pickle.dump(self, _file, pickle.HIGHEST_PROTOCOL)
+        finally:
+            self.ode, self.solver, self.f = ode, solver, f
+            if objs is not None:
+                self.objs = None
+                objs['kwargs']['pool'] = pool
+            if mdl is not None:
+                self.mdl = None
+
+    def load_int_dump(self, other, cstm_mdl_name=None, add_model=False, **kwargs):
+        """Resumes the run stored in `other` (an unpickled intermediate dump) -- parareal.py:141-189.  `ode`,
+        `solver` and `pool` come from this object / kwargs (they are not in the dump)."""
+        self.tspan, self.n, self.N, self.epsilon = other.tspan, other.n, other.N, other.epsilon
+        self.runs, self.fine, self.ode_name, self.verbose = other.runs, other.fine, other.ode_name, other.verbose
+        self.ode = kwargs.pop('ode', self.ode)
+        self.solver = kwargs.pop('solver', self.solver)
+        if self.ode is None or self.solver is None:
+            raise Exception('ode and solver must be given to resume: they are not stored in the dump')
+        if self.ode_name != self.ode.name or self.n != self.ode.get_dim():
+            raise Exception('Input and previous ODEs do not match')
+        self.f = self.ode.get_vector_field()
+        self.u0 = self.ode.get_init_cond()
+        objs = other.objs
+        run_kwargs = dict(objs['kwargs'])
+        run_kwargs.update(kwargs)
+        mdl = other.mdl
+        base_time = objs['F_time'] + objs['G_time'] + mdl.get_times()['mdl_tot_t']
+        return self.run(mdl, base_time, cstm_mdl_name, add_model, _run_from_int=True, _reload_objs=objs, **run_kwargs)
+
+    def _run_from_int(self, mdl, base_time, cstm_mdl_name, add_model, **kwargs):
+        """parareal.py:192-209"""
+        mdl.restore_attrs(kwargs['pool'])
+        s_time = time.time()
+        out = self._parareal(mdl, _load_mdl=True, **kwargs)
+        elap_time = time.time() - s_time + base_time
+        out['timings']['runtime'] = elap_time
+        if add_model:
+            out['mdl'] = mdl.store()
+        self.runs[mdl.name if cstm_mdl_name is None else cstm_mdl_name] = out
         return out
 
     def _make_model(self, model, **kwargs):
@@ -113,9 +176,8 @@ class Parareal():
         return out
 
     # the iteration of parareal.py:212-471, state kept as in PararealLight (:851-862)
-    def _parareal(self, model, debug=False, early_stop=None, parall='Serial', store_int=False, **kwargs):
-        if store_int:
-            raise NotImplementedError('intermediate checkpoints are outside the hot path (SURVEY.md section 8f)')
+    def _parareal(self, model, debug=False, early_stop=None, parall='Serial', store_int=False, _load_mdl=False,
+                  _reload_objs=None, **kwargs):
         N, eps, n = self.N, self.epsilon, self.n
         solver = self.solver
         t = np.linspace(self.tspan[0], self.tspan[1], num=N + 1)
@@ -131,19 +193,31 @@ class Parareal():
         for a in cur.values():
             a[0] = self.u0
         G_time = F_time = F_time_serial = 0
-        # coarse initialisation (parareal.py:264-277)
-        state = self.u0
-        for i in range(N):
-            state, secs = solver.run_G_timed(t[i], t[i + 1], state)
-            G_time += secs
-            cur['uG'][i + 1] = state
-        cur['u'][:] = cur['uG']
-        nxt = {key: a.copy() for key, a in cur.items()}
-        history = [cur['u'].copy()]
-        x = np.zeros((0, n))
-        D = np.zeros((0, n))
-        k = 0
-        for k in range(N):
+        k0 = 0
+        if _load_mdl:
+            # resume (parareal.py:279-297): state after iteration k of the stored run
+            o = _reload_objs
+            I, conv_int, err = o['I'], list(o['conv_int']), o['err'].copy()
+            cur = {key: o[key].copy() for key in ('u', 'uG', 'uF')}
+            nxt = {key: a.copy() for key, a in cur.items()}
+            history = [h.copy() for h in o['history']]
+            x, D = o['x'].copy(), o['D'].copy()
+            G_time, F_time, F_time_serial = o['G_time'], o['F_time'], o.get('F_time_serial', 0)
+            k0 = o['k'] + 1
+        else:
+            # coarse initialisation (parareal.py:264-277)
+            state = self.u0
+            for i in range(N):
+                state, secs = solver.run_G_timed(t[i], t[i + 1], state)
+                G_time += secs
+                cur['uG'][i + 1] = state
+            cur['u'][:] = cur['uG']
+            nxt = {key: a.copy() for key, a in cur.items()}
+            history = [cur['u'].copy()]
+            x = np.zeros((0, n))
+            D = np.zeros((0, n))
+        k = max(k0 - 1, 0)
+        for k in range(k0, N):
             if verbose == 'v':
                 print(f'{self.ode_name} {model.name} iteration number (out of {N}): {k+1} ')
             s_time = time.time()
@@ -198,6 +272,18 @@ class Parareal():
             if verbose == 'v':
                 print('--> Converged:', I)
             conv_int.append(I)
+            if store_int:
+                # parareal.py:420-431; the state is kept PararealLight-style (current iterate + history of u),
+                # so the dump holds u / uG / uF of iteration k+1 rather than the (N+1, d, k+2) arrays
+                name_base = kwargs.get('int_name', f'{self.ode_name}_{self.N}_{model.name}_int')
+                int_dir = kwargs.get('int_dir', '')
+                _objs = {'t': t, 'I': I, 'verbose': verbose, 'u': cur['u'], 'uG': cur['uG'], 'uF': cur['uF'],
+                         'history': history, 'err': err, 'x': x, 'D': D, 'G_time': G_time, 'F_time': F_time,
+                         'F_time_serial': F_time_serial, 'debug': debug, 'early_stop': early_stop, 'parall': parall,
+                         'store_int': store_int, 'kwargs': dict(kwargs, debug=debug, early_stop=early_stop,
+                                                                parall=parall, store_int=store_int),
+                         'k': k, 'conv_int': conv_int}
+                self.store(path=os.path.join(int_dir, name_base), name=f'{name_base}_{k}', mdl=model, objs=_objs)
             if I == N:
                 break
             if (early_stop is not None) and k == (early_stop - 1):

@@ -145,3 +145,22 @@ def test_dimension_sharded_sweep_equals_replicated_sweep_bitwise():
     with pytest.raises(_lib.NNGPError, match="outside"):
         h.sweep_shard(st['sys'], st['mG'], p.solver.h_mode, p.solver.Ng, st['t'], N, I, I, 1, m, 1, starts, 0.1, 0.1,
                       ref_u, ref_g, n, 24, 16, st['stream'])
+
+
+def test_checkpoint_and_resume_nngp_host_driver(tmp_path):
+    """store_int / load_int_dump with the nnGP model on the device: the dump carries the model copy (dataset on
+    the host, NumPy generator state), the resumed run re-uploads the dataset, draws the same Nelder-Mead starts
+    and ends bit-identically to the uninterrupted run"""
+    import pickle
+    z, cfg, mkw, p = build("lorenz_N32_m11", nn.Parareal)
+    full = p.run(model='nngp', **mkw)
+    z, cfg, mkw, p2 = build("lorenz_N32_m11", nn.Parareal)
+    part = p2.run(model='nngp', early_stop=4, store_int=True, int_dir=str(tmp_path), int_name='ck', **mkw)
+    assert part['k'] == 4
+    with open(tmp_path / 'ck' / 'ck_3', 'rb') as fh:
+        dump = pickle.load(fh)
+    z, cfg, mkw, p3 = build("lorenz_N32_m11", nn.Parareal)
+    res = p3.load_int_dump(dump)
+    assert res['k'] == full['k'] and res['conv_int'] == full['conv_int']
+    assert np.array_equal(res['u_last'], full['u_last'])
+    assert np.array_equal(res['err'], full['err'], equal_nan=True)

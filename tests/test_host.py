@@ -255,3 +255,40 @@ def test_bench_reference_arm_contract():
     assert line["config"]["N_slices"] == 16 and line["config"]["d"] == 32
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_intermediate_checkpoint_and_resume_host_driver(tmp_path):
+    """parareal.py:114-209, 420-431 in the host mirror: `store_int=True` dumps the loop state after every iteration,
+    `load_int_dump` resumes it; the resumed run ends exactly like the uninterrupted one.  CPU: a NumPy solver
+    (oracle RK on the Lorenz field) behind the SolverAbstr protocol, the plain Parareal model."""
+    import pickle
+    from oracle import rk as ork, systems as osys
+    from nearest_neighbors_gparareal_b200.solver import SolverAbstr
+    o = osys.Lorenz(normalization='-11')
+
+    class NpSolver(SolverAbstr):
+        def run_F(self, t0, t1, u0):
+            return ork.rk_last(o.f, 'RK4', t0, t1, 60, np.asarray(u0, dtype=float))
+
+        def run_G(self, t0, t1, u0):
+            return ork.rk_last(o.f, 'RK1', t0, t1, 6, np.asarray(u0, dtype=float))
+
+    def driver():
+        return nn.Parareal(nn.Lorenz(normalization='-11'), NpSolver(), tspan=[0, 1.0], N=10, epsilon=1e-10, verbose='')
+
+    full = driver().run(model='parareal', pool=nn.MyPool())
+    assert full['converged'] and full['k'] > 4
+    part = driver().run(model='parareal', pool=nn.MyPool(), early_stop=3, store_int=True, int_dir=str(tmp_path),
+                        int_name='ck')
+    assert part['k'] == 3 and not part['converged']
+    with open(tmp_path / 'ck' / 'ck_2', 'rb') as fh:
+        dump = pickle.load(fh)
+    assert dump.ode is None and dump.solver is None and dump.objs['k'] == 2 and dump.objs['kwargs']['pool'] is None
+    p3 = driver()
+    res = p3.load_int_dump(dump, pool=nn.MyPool())
+    assert res['k'] == full['k'] and res['conv_int'] == full['conv_int'] and res['converged']
+    assert np.array_equal(res['u_last'], full['u_last'])
+    assert np.array_equal(res['err'], full['err'], equal_nan=True)
+    assert np.array_equal(res['u'], full['u'])            # the history of iterates is restored too
+    with pytest.raises(Exception, match='do not match'):
+        nn.Parareal(nn.Rossler(), NpSolver(), tspan=[0, 1.0], N=10, verbose='').load_int_dump(dump, pool=nn.MyPool())
