@@ -77,6 +77,14 @@ def load_library():
     global _lib
     with _lock:
         if _lib is None:
+            if not os.path.exists(LIB_PATH) and "NNGPARA_LIB" not in os.environ:
+                # not built yet (fresh checkout): compile in-tree with nvcc -- never a CPU fallback
+                try:
+                    from .build import build
+                    build()
+                except Exception as exc:
+                    raise NNGPError(f"{LIB_PATH} is missing and could not be built ({exc}); run "
+                                    "`python __graft_entry__.py` (build()) first; there is no CPU fallback")
             if not os.path.exists(LIB_PATH):
                 raise NNGPError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
                                 "there is no CPU fallback")
