@@ -81,6 +81,13 @@ int nngp_rk_batch(nngp_handle_t h, int sys, int method, int h_mode, long long st
 int nngp_rk_batch_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps,
                        int n_slices, const double* t0, const double* t1, const double* u0,
                        double* u1);
+/* Every step of the solve: RK.run (RK.py:91-99), what SolverRK.run_F_full / run_G_full return (solver.py:109-113).
+ * d_traj[n_slices][steps+1][d] (row 0 = u0); the host variant solves one slice, traj[steps+1][d]. */
+int nngp_rk_full(nngp_handle_t h, int sys, int method, int h_mode, long long steps, int n_slices,
+                 const double* d_t0, const double* d_t1, const double* d_u0, long long ld_u0, double* d_traj,
+                 void* stream);
+int nngp_rk_full_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps, double t0, double t1,
+                      const double* u0, double* traj);
 /* the Butcher tableau the kernels use (a[S*S] row-major, b[S], c[S]); RK.py:30-48 */
 int nngp_get_tableau(int method, int* stages, double* a, double* b, double* c);
 

@@ -34,6 +34,8 @@ SIGNATURES = {
     "nngp_rhs_eval_host": (ci, [vp, ci, ci, vp, vp]),
     "nngp_rk_batch": (ci, [vp, ci, ci, ci, cll, ci, vp, vp, vp, cll, vp, cll, vp]),
     "nngp_rk_batch_host": (ci, [vp, ci, ci, ci, cll, ci, vp, vp, vp, vp]),
+    "nngp_rk_full": (ci, [vp, ci, ci, ci, cll, ci, vp, vp, vp, cll, vp, vp]),
+    "nngp_rk_full_host": (ci, [vp, ci, ci, ci, cll, cd, cd, vp, vp]),
     "nngp_get_tableau": (ci, [ci, c_int_p, vp, vp, vp]),
     "nngp_dataset_reserve": (ci, [vp, cll, ci]),
     "nngp_dataset_reset": (ci, [vp]),
@@ -167,6 +169,13 @@ class Handle:
         self.check(self.lib.nngp_rk_batch_host(self.h, sys, method, h_mode, int(steps), t0.shape[0],
                                                _ptr(t0), _ptr(t1), _ptr(u0), _ptr(u1)))
         return u1
+
+    def rk_full_host(self, sys, method, h_mode, steps, t0, t1, u0):
+        u0 = as_f64(u0).ravel()
+        traj = np.empty((int(steps) + 1, u0.shape[0]))
+        self.check(self.lib.nngp_rk_full_host(self.h, sys, method, h_mode, int(steps), float(t0), float(t1),
+                                              _ptr(u0), _ptr(traj)))
+        return traj
 
     def rk_batch(self, sys, method, h_mode, steps, n, d_t0, d_t1, d_u0, ld0, d_u1, ld1, stream=None):
         self.check(self.lib.nngp_rk_batch(self.h, sys, method, h_mode, int(steps), int(n), _ptr(d_t0),

@@ -327,6 +327,42 @@ int nngp_rk_batch_host(nngp_handle_t h, int sys, int method, int h_mode, long lo
   return 0;
 }
 
+// every step of n_slices solves: d_traj[n_slices][steps+1][d]  (RK.run, RK.py:91-99)
+int nngp_rk_full(nngp_handle_t h, int sys, int method, int h_mode, long long steps, int n_slices,
+                 const double* d_t0, const double* d_t1, const double* d_u0, long long ld_u0, double* d_traj,
+                 void* stream) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  if (n_slices <= 0) return 0;
+  if (!d_traj) return nngp_fail(h, "rk_full: d_traj is NULL");
+  if (steps < 1) return nngp_fail(h, "steps must be >= 1 (got %lld)", steps);
+  // the last state also goes to the last row of each trajectory: use it as the u1 buffer
+  double* u1 = d_traj + (long long)steps * s->d;
+  return rk_launch(h, *s, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, u1, (steps + 1) * (long long)s->d,
+                   as_stream(stream), d_traj);
+}
+
+int nngp_rk_full_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps, double t0, double t1,
+                      const double* u0, double* traj) {
+  const SystemDesc* s;
+  if (int rc = get_sys(h, sys, &s)) return rc;
+  if (steps < 1) return nngp_fail(h, "steps must be >= 1 (got %lld)", steps);
+  const int d = s->d;
+  const size_t nb_u = sizeof(double) * d, nb_tr = sizeof(double) * (size_t)(steps + 1) * d;
+  char* dev = (char*)stage_buf(h, 2 * Carver::pad(sizeof(double)) + Carver::pad(nb_u) + Carver::pad(nb_tr));
+  if (!dev) return nngp_fail(h, "rk_full_host: out of device memory (%zu bytes)", nb_tr);
+  Carver cd(dev);
+  double* g_t0 = cd.take<double>(1); double* g_t1 = cd.take<double>(1);
+  double* g_u0 = cd.take<double>(d); double* g_tr = cd.take<double>((size_t)(steps + 1) * d);
+  NNGP_CUDA(h, cudaMemcpyAsync(g_t0, &t0, sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+  NNGP_CUDA(h, cudaMemcpyAsync(g_t1, &t1, sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+  NNGP_CUDA(h, cudaMemcpyAsync(g_u0, u0, nb_u, cudaMemcpyHostToDevice, h->own_stream));
+  if (int rc = nngp_rk_full(h, sys, method, h_mode, steps, 1, g_t0, g_t1, g_u0, d, g_tr, h->own_stream)) return rc;
+  NNGP_CUDA(h, cudaMemcpyAsync(traj, g_tr, nb_tr, cudaMemcpyDeviceToHost, h->own_stream));
+  NNGP_CUDA(h, cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
 int nngp_get_tableau(int method, int* stages, double* a, double* b, double* c) {
   if (method != 1 && method != 2 && method != 4 && method != 8) return -1;
   rk_host_tableau(method, stages, a, b, c);

@@ -29,6 +29,7 @@ struct SysArgs {
   int normalize;
   double p[NNGP_MAX_PARAMS];
   double q[4];  // derived parameters (rk.cu)
+  double* traj;  // optional: state after every step, [n_slices][steps+1][d] (run_F_full); nullptr = last state only
   const double* mn;
   const double* mx;
 };
@@ -94,7 +95,7 @@ SysArgs nngp_sys_args(const SystemDesc& s);
 int rk_set_tableaus(nngp_handle_t h);
 int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long long steps,
               int n_slices, const double* d_t0, const double* d_t1, const double* d_u0,
-              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st);
+              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st, double* d_traj = nullptr);
 int rhs_launch(nngp_handle_t h, const SystemDesc& s, int n, const double* d_u, double* d_out,
                cudaStream_t st);
 void rk_host_tableau(int method, int* S, double* a, double* b, double* c);

@@ -296,6 +296,11 @@ rk_small_kernel(SysArgs A, int h_mode, long long steps, int n_slices,
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
   double k[D][S];
+  double* traj = A.traj ? A.traj + (long long)s * (steps + 1) * D : nullptr;
+  if (traj) {
+#pragma unroll
+    for (int i = 0; i < D; i++) traj[i] = u[i];
+  }
   for (long long n = 0; n < steps; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
 #pragma unroll
@@ -315,6 +320,10 @@ rk_small_kernel(SysArgs A, int h_mode, long long steps, int n_slices,
     }
 #pragma unroll
     for (int c = 0; c < D; c++) u[c] = u[c] + numpy_sum_bk<S>(k[c], T.b);
+    if (traj) {
+#pragma unroll
+      for (int c = 0; c < D; c++) traj[(n + 1) * D + c] = u[c];
+    }
   }
 #pragma unroll
   for (int i = 0; i < D; i++) u1[s * ld1 + i] = u[i];
@@ -456,6 +465,11 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
   int par = 0;
+  double* traj = A.traj ? A.traj + s * (steps + 1) * A.d : nullptr;
+  if (traj && active) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) traj[c * npts + p] = u[c];
+  }
   for (long long n = 0; n < steps; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
     double hs[NC], hv[3];
@@ -487,6 +501,10 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
       for (int i = 0; i < S; i++)
         if (b_nonzero<S>(i)) u[c] = fma(T.b[i], k[c][i], u[c]);
     }
+    if (traj && active) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) traj[(n + 1) * A.d + c * npts + p] = u[c];
+    }
   }
   if (active) {
 #pragma unroll
@@ -510,7 +528,7 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
 template <int TY, int TB>
 struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) : ((TB <= 128) ? 2 : 1); };
 
-template <int S, int TY, int TB>
+template <int S, int TY, int TB, bool TRAJ>
 __global__ void __launch_bounds__(TB, TileOcc<TY, TB>::value)
 rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long long task0, int n_chunks,
                    const double* __restrict__ t0s, const double* __restrict__ t1s,
@@ -547,6 +565,17 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
   const double t0 = t0s[s], t1 = t1s[s];
   const double step = (t1 - t0) / (double)steps;
   int par = 0;
+  double* traj = TRAJ ? A.traj + s * (steps + 1) * (2 * npts) : nullptr;  // TRAJ: run_F_full, every step stored
+  auto put = [&](long long row) {
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int r = 0; r < TY; r++) {
+        traj[row * (2 * npts) + c * npts + o00 + r * dx] = u[c][2 * r];
+        traj[row * (2 * npts) + c * npts + o00 + r * dx + 1] = u[c][2 * r + 1];
+      }
+  };
+  if (TRAJ && active && n_begin == 0) put(0);
   for (long long n = n_begin; n < n_end; n++) {
     const double h = step_size(h_mode, t0, t1, step, n, steps);
     double hv[3];
@@ -632,6 +661,7 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
 #pragma unroll
         for (int i = 0; i < S; i++)
           if (b_nonzero<S>(i)) u[c][q] = fma(T.b[i], k[c][q][i], u[c][q]);
+    if (TRAJ && active) put(n + 1);
   }
   if (active) {
 #pragma unroll
@@ -662,8 +692,12 @@ static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long s
   const size_t smem = 2 * sizeof(double) * 2 * npts;
   const int per_launch = 2 * sms;
   const char* force = getenv("NNGP_RK_CHUNKS");  // experiments: 0 = never chunk
+  if (A.traj != nullptr) {  // every step stored (run_F_full): one launch
+    rk_fhn_tile_kernel<S, TY, TB, true><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
+    return 1;
+  }
   if (TB > 64 || n <= per_launch || steps < 4096 || (force && force[0] == '0')) {
-    rk_fhn_tile_kernel<S, TY, TB><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
+    rk_fhn_tile_kernel<S, TY, TB, false><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
     return 1;
   }
   // chunks: the smallest count >= 24 that fills the last launch, else 32
@@ -676,14 +710,14 @@ static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long s
   const size_t smem2 = 80 * 1024;  // > 1/3 of the SM's shared memory: at most two CTAs per SM
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(rk_fhn_tile_kernel<S, TY, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaFuncSetAttribute(rk_fhn_tile_kernel<S, TY, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     attr_set = true;
   }
   const long long total = (long long)n * chunks;
   int launches = 0;
   for (long long task0 = 0; task0 < total; task0 += per_launch) {
     const int grid = (int)((total - task0 < per_launch) ? total - task0 : per_launch);
-    rk_fhn_tile_kernel<S, TY, TB><<<grid, threads, smem2, st>>>(A, h_mode, steps, n, task0, chunks, t0, t1, u0, ld0, u1, ld1);
+    rk_fhn_tile_kernel<S, TY, TB, false><<<grid, threads, smem2, st>>>(A, h_mode, steps, n, task0, chunks, t0, t1, u0, ld0, u1, ld1);
     launches++;
   }
   return launches;
@@ -741,6 +775,7 @@ SysArgs nngp_sys_args(const SystemDesc& s) {
   A.normalize = s.normalize;
   for (int i = 0; i < NNGP_MAX_PARAMS; i++) A.p[i] = s.params[i];
   for (int i = 0; i < 4; i++) A.q[i] = 0.0;
+  A.traj = nullptr;
   if (s.system_id == NNGP_SYS_FHN_PDE) {  // see FhnPde::eval_k
     A.q[0] = s.params[1] + 1.0;
     A.q[1] = s.params[4] * s.params[6];
@@ -822,7 +857,7 @@ static int check_system(nngp_handle_t h, const SystemDesc& s, int* npts) {
 
 int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long long steps,
               int n_slices, const double* d_t0, const double* d_t1, const double* d_u0,
-              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st) {
+              long long ld_u0, double* d_u1, long long ld_u1, cudaStream_t st, double* d_traj) {
   const int slot = method_slot(method);
   if (slot < 0) return nngp_fail(h, "Only RK1, RK2, RK4 and RK8 are implemented (got %d)", method);
   if (steps < 1) return nngp_fail(h, "steps must be >= 1 (got %lld)", steps);
@@ -830,7 +865,8 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
   if (n_slices <= 0) return 0;
   int npts = 0;
   if (int rc = check_system(h, s, &npts)) return rc;
-  const SysArgs A = nngp_sys_args(s);
+  SysArgs A = nngp_sys_args(s);
+  A.traj = d_traj;
   ProfScope prof(h, 0, st);
 #define SMALL(SYS) launch_small<SYS>(A, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1, st)
   switch (s.system_id) {

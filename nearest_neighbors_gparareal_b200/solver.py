@@ -114,6 +114,16 @@ class CudaSolverRK(SolverAbstr):
     def run_G(self, t0, t1, u0):
         return self._batch(self.G, self.Ng, [t0], [t1], np.asarray(u0, dtype=float)[None, :])[0]
 
+    def run_F_full(self, t0, t1, u0):
+        """solver.py:109-110: every step of the fine solve, ndarray[Nf+1, d]"""
+        h, sys = self.device()
+        return h.rk_full_host(sys, _lib.METHODS[self.F], self.h_mode, self.Nf, t0, t1, u0)
+
+    def run_G_full(self, t0, t1, u0):
+        """solver.py:112-113"""
+        h, sys = self.device()
+        return h.rk_full_host(sys, _lib.METHODS[self.G], self.h_mode, self.Ng, t0, t1, u0)
+
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_handle'] = None

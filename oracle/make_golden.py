@@ -203,14 +203,42 @@ def published():
                         if "error" in str(v)[:12] or isinstance(v, list)}, flush=True)
 
 
+def rk_full_vectors():
+    """Known answers of RK.run (`_RK_numpy_`, every step): what SolverRK.run_F_full / run_G_full return."""
+    ns = load_reference()
+    S = ns.systems
+    rng = np.random.default_rng(11)
+    out = {}
+    systems = {
+        "lorenz": S.Lorenz(normalization="-11", use_jax=False),
+        "hopf": S.Hopf(normalization="-11", use_jax=False),
+        "burgers32": S.Burgers(d_x=32, normalization="-11", use_jax=False),
+        "fhn4": S.FHN_PDE(d_x=4, use_jax=False),
+        "fhn6": S.FHN_PDE(d_x=6, use_jax=False),
+    }
+    for name, ode in systems.items():
+        f = ode.get_vector_field()
+        u0 = ode.get_init_cond() + 0.01 * rng.standard_normal(ode.get_dim())
+        out[f"{name}_u0"] = u0
+        for method, steps in (("RK1", 9), ("RK4", 7), ("RK8", 12)):
+            rk = ns.RK.RK(f, method, use_jax=False)
+            t0, t1 = 0.21, 0.21 + (0.4 if u0.shape[0] < 10 else 0.06)
+            out[f"{name}_{method}_t"] = np.array([t0, t1, steps])
+            out[f"{name}_{method}_traj"] = rk.run(t0, t1, steps, u0)
+    np.savez_compressed(os.path.join(OUT, "rk_full_vectors.npz"), **out)
+    print("rk_full_vectors", len(out), flush=True)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     todo = sys.argv[1:] or ["all"]
     if todo == ["all"]:
-        todo = ["rk_vectors", "published"] + list(CASES)
+        todo = ["rk_vectors", "rk_full_vectors", "published"] + list(CASES)
     for item in todo:
         if item == "rk_vectors":
             rk_vectors()
+        elif item == "rk_full_vectors":
+            rk_full_vectors()
         elif item == "published":
             published()
         else:

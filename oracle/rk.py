@@ -48,7 +48,7 @@ def tableau(method):
     return np.array(a, dtype=float), np.array(b, dtype=float), np.array(c, dtype=float)
 
 
-def rk_last(f, method, t0, t1, steps, u0, h_mode="linspace"):
+def rk_last(f, method, t0, t1, steps, u0, h_mode="linspace", _full=False):
     """u(t1) after `steps` explicit RK steps from u(t0)=u0.
 
     h_mode='linspace' : the NumPy path, RK.py:91-99 + 113-137 -- node times come
@@ -71,6 +71,7 @@ def rk_last(f, method, t0, t1, steps, u0, h_mode="linspace"):
         dt = (t1 - t0) / steps
         t = t0
     brow = b.reshape(1, S)
+    traj = [u.copy()] if _full else None
     for n in range(steps):
         if h_mode == "linspace":
             t = tt[n]
@@ -85,6 +86,14 @@ def rk_last(f, method, t0, t1, steps, u0, h_mode="linspace"):
                 temp = temp + a[i, j] * k[:, j]
             k[:, i] = h * f(t + c[i] * h, u + temp)
         u = u + np.sum(brow * k, 1)
+        if _full:
+            traj.append(u.copy())
         if h_mode != "linspace":
             t = t + dt
-    return u
+    return np.stack(traj) if _full else u
+
+
+def rk_full(f, method, t0, t1, steps, u0):
+    """Every step of the solve, [steps+1, d] -- reference RK.run (RK.py:91-99) with the NumPy branch
+    `_RK_numpy_` (RK.py:113-137); what SolverRK.run_F_full / run_G_full return (solver.py:109-113)."""
+    return rk_last(f, method, t0, t1, steps, u0, "linspace", _full=True)

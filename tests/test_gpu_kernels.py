@@ -150,6 +150,31 @@ def test_fhn_time_chunked_fine_step_equals_single_launch_bitwise():
         assert np.all(np.isfinite(got)) and np.array_equal(got, ref), h_mode
 
 
+@pytest.mark.parametrize("name", ["lorenz", "hopf", "burgers32", "fhn4", "fhn6"])
+def test_rk_full_trajectory_vs_reference_vectors(name):
+    """CudaSolverRK.run_F_full / run_G_full (solver.py:109-113): every step of the solve against the trajectories
+    recorded from the reference's RK.run -- bit-exact for the closed-form systems, 1e-11 scaled for the PDE stencils;
+    the last row is the bits of run_F"""
+    z = np.load(os.path.join(GOLDEN, "rk_full_vectors.npz"))
+    mk = {"lorenz": lambda: nn.Lorenz(normalization='-11'), "hopf": lambda: nn.Hopf(normalization='-11'),
+          "burgers32": lambda: nn.Burgers(d_x=32, normalization='-11'), "fhn4": lambda: nn.FHN_PDE(d_x=4),
+          "fhn6": lambda: nn.FHN_PDE(d_x=6)}[name]
+    ode = mk()
+    u0 = z[f"{name}_u0"]
+    for method in ("RK1", "RK4", "RK8"):
+        t0, t1, steps = z[f"{name}_{method}_t"]
+        s = nn.CudaSolverRK(ode.get_vector_field(), Ng=int(steps), Nf=int(steps), F=method, G=method)
+        got = s.run_F_full(t0, t1, u0)
+        want = z[f"{name}_{method}_traj"]
+        assert got.shape == want.shape
+        if name in ("lorenz", "hopf"):
+            assert np.array_equal(got, want), method
+        else:
+            assert scaled_err(got, want) < 1e-11, method
+        assert np.array_equal(got[0], u0) and np.array_equal(got[-1], s.run_F(t0, t1, u0))
+        assert np.array_equal(s.run_G_full(t0, t1, u0), got)
+
+
 def test_rk_errors(handle):
     ode = nn.Burgers(d_x=2000, normalization='-11')
     s = nn.CudaSolverRK(ode.get_vector_field(), Ng=1, Nf=1, F='RK4', G='RK1')

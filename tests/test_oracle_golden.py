@@ -46,6 +46,25 @@ def test_vector_field_and_rk_bitwise(rkv, name):
         assert np.array_equal(got, rkv[f"{name}_{method}_u1"]), method
 
 
+FULL_SYSTEMS = {"lorenz": lambda: osys.Lorenz(normalization="-11"), "hopf": lambda: osys.Hopf(normalization="-11"),
+                "burgers32": lambda: osys.Burgers(d_x=32, normalization="-11"), "fhn4": lambda: osys.FHN_PDE(d_x=4),
+                "fhn6": lambda: osys.FHN_PDE(d_x=6)}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SYSTEMS))
+def test_rk_full_trajectory_bitwise(name):
+    """oracle rk_full == reference RK.run (`_RK_numpy_`, every step; solver.py:109-113 run_F_full), bit for bit"""
+    z = np.load(os.path.join(GOLDEN, "rk_full_vectors.npz"))
+    s = FULL_SYSTEMS[name]()
+    for method in ("RK1", "RK4", "RK8"):
+        t0, t1, steps = z[f"{name}_{method}_t"]
+        got = ork.rk_full(s.f, method, t0, t1, int(steps), z[f"{name}_u0"])
+        want = z[f"{name}_{method}_traj"]
+        assert got.shape == want.shape == (int(steps) + 1, z[f"{name}_u0"].shape[0])
+        assert np.array_equal(got, want), method
+        assert np.array_equal(got[-1], ork.rk_last(s.f, method, t0, t1, int(steps), z[f"{name}_u0"]))
+
+
 def test_presets_match_reference_configs():
     """configs.py presets recorded with the golden runs"""
     z, cfg, _ = load_run("lorenz_N50_m11")
