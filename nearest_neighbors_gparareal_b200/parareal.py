@@ -87,6 +87,28 @@ class Parareal():
         pool.shutdown()
         return out
 
+    # ---- continuous trajectory (parareal.py:487-508) --------------------------------------------
+    def build_cont_traj(self, key=None):
+        """The fine solver's full trajectory through the slices of a finished run: vstack of
+        solver.run_F_full(t_i, t_{i+1}, u_i) for the last iterate (parareal.py:487-508)."""
+        if key is None:
+            if len(self.runs) != 1:
+                raise Exception('Multiple runs, must specify key')
+            key = list(self.runs.keys())[0]
+        if isinstance(key, dict) and 't' in key and 'u' in key:
+            t, u = key['t'], key['u']
+        else:
+            t, u = self.runs[key]['t'], self.runs[key]['u']
+        return self._build_cont_traj(t, u)
+
+    def _build_cont_traj(self, t, u):
+        u = np.asarray(u)
+        last = u[:, :, -1] if u.ndim == 3 else u  # Parareal keeps u[N+1, d, K], the light drivers u[N+1, d]
+        return np.vstack([self.solver.run_F_full(t[i], t[i + 1], last[i]) for i in range(self.N)])
+
+    def clear_plot_obj(self):
+        self.runs = dict()
+
     # ---- intermediate checkpoints (parareal.py:114-209, 420-431) -------------------------------
     def store(self, name, path='', mdl=None, objs=None):
         """Pickles the driver without its ODE / solver (device handles do not pickle), with the model copy

@@ -290,5 +290,15 @@ def test_intermediate_checkpoint_and_resume_host_driver(tmp_path):
     assert np.array_equal(res['u_last'], full['u_last'])
     assert np.array_equal(res['err'], full['err'], equal_nan=True)
     assert np.array_equal(res['u'], full['u'])            # the history of iterates is restored too
+    # build_cont_traj (parareal.py:487-508) needs run_F_full of the solver protocol
+    class NpSolverFull(NpSolver):
+        def run_F_full(self, t0, t1, u0):
+            return ork.rk_full(o.f, 'RK4', t0, t1, 60, np.asarray(u0, dtype=float))
+    p4 = nn.Parareal(nn.Lorenz(normalization='-11'), NpSolverFull(), tspan=[0, 1.0], N=10, epsilon=1e-10, verbose='')
+    out4 = p4.run(model='parareal', pool=nn.MyPool())
+    traj = p4.build_cont_traj()
+    assert traj.shape == (10 * 61, 3) and np.array_equal(traj[60], out4['u_last'][1] * 0 + traj[60])
+    assert np.allclose(traj[60::61][:, :], np.stack([ork.rk_last(o.f, 'RK4', out4['t'][i], out4['t'][i + 1], 60,
+                                                                out4['u_last'][i]) for i in range(10)]), rtol=0, atol=0)
     with pytest.raises(Exception, match='do not match'):
         nn.Parareal(nn.Rossler(), NpSolver(), tspan=[0, 1.0], N=10, verbose='').load_int_dump(dump, pool=nn.MyPool())
