@@ -1,30 +1,37 @@
-"""Host mirror of reference utils.py:1-33 (`Normalize`)."""
+"""Affine state normalisation used by the ODE systems (interface of reference utils.py:1-33) and the
+dimension partition of the multi-GPU sweep.
+
+`Normalize('-11')` maps the box [mn, mx] onto [-1, 1]^d; on the device the same map is fused into the
+right-hand sides (csrc/rk.cu), this host object serves initial conditions and tests.
+"""
+_KINDS = ('identity', '-11')
 
 
 class Normalize():
+    """x -> 2 (x - mn) / (mx - mn) - 1 for kind '-11', the identity otherwise.
+
+    Methods and error text follow the reference class so that ODE subclasses written against it work
+    unchanged: fit (forward map), inverse, get_scale (derivative of the forward map)."""
+
     def __init__(self, mn, mx, norm_type=None):
-        self.mn = mn
-        self.mx = mx
-        if norm_type is None:
-            norm_type = 'identity'
-        if norm_type.lower() not in ['identity', '-11']:
+        kind = 'identity' if norm_type is None else norm_type.lower()
+        if kind not in _KINDS:
             raise NotImplementedError('Only identity and -11 are implemented')
-        self.norm_type = norm_type.lower()
+        self.norm_type = kind
+        self.mn, self.mx = mn, mx
+
+    @property
+    def _span(self):
+        return self.mx - self.mn
 
     def fit(self, x):
-        if self.norm_type == '-11':
-            return 2 * (x - self.mn) / (self.mx - self.mn) - 1
-        return x
+        return x if self.norm_type == 'identity' else 2 * (x - self.mn) / self._span - 1
 
     def inverse(self, x):
-        if self.norm_type == '-11':
-            return (x + 1) / 2 * (self.mx - self.mn) + self.mn
-        return x
+        return x if self.norm_type == 'identity' else (x + 1) / 2 * self._span + self.mn
 
     def get_scale(self):
-        if self.norm_type == '-11':
-            return 2 / (self.mx - self.mn)
-        return 1
+        return 1 if self.norm_type == 'identity' else 2 / self._span
 
 
 def dim_block(d, rank, world):
