@@ -164,3 +164,15 @@ def test_checkpoint_and_resume_nngp_host_driver(tmp_path):
     assert res['k'] == full['k'] and res['conv_int'] == full['conv_int']
     assert np.array_equal(res['u_last'], full['u_last'])
     assert np.array_equal(res['err'], full['err'], equal_nan=True)
+
+
+def test_device_dataset_grows_when_capacity_is_exceeded():
+    """the device dataset (X, Y, transposed X) is re-allocated and copied when an iteration's rows no longer fit
+    (nngp_dataset_reserve): a run that starts with room for one iteration only equals the default run bit for bit"""
+    z, cfg, mkw, p = build("lorenz_N32_m11", nn.PararealDevice)
+    ref = p.run(model='nngp', **mkw)
+    z, cfg, mkw, p2 = build("lorenz_N32_m11", nn.PararealDevice)
+    out = p2.run(model='nngp', max_rows=33, **mkw)
+    assert out['n_rows'] == ref['n_rows'] > 33 * 3
+    assert out['k'] == ref['k'] and out['conv_int'] == ref['conv_int']
+    assert np.array_equal(out['u'], ref['u']) and np.array_equal(out['err'], ref['err'], equal_nan=True)
