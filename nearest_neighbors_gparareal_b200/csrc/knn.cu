@@ -12,9 +12,11 @@
 //
 // Layout: the dataset is kept twice, row-major X[cap,d] (row gathers for the GP) and
 // transposed XT[d,cap] so that a warp scanning 32 consecutive rows reads 32 consecutive
-// doubles per coordinate.  One thread owns one row (times TQ queries); selection keeps a
-// sorted top-m list spread over the lanes of a warp (lane l = l-th smallest) and inserts
-// with ballot + shuffle; the per-warp lists of a CTA are merged by ranking in shared memory.
+// doubles per coordinate.  One thread owns one row (times TQ queries; the one-query kernel
+// prefetches 16 coordinates ahead of the serial addition chain); selection keeps a sorted top-m
+// list spread over the lanes of a warp (lane l = l-th smallest), inserts a few survivors of a
+// round with ballot + shuffle and sorts / merges many with a bitonic network; warp 0 merges the
+// per-warp lists; few queries over many rows select in two levels (chunks, then candidates).
 #include "common.cuh"
 
 #include <cfloat>

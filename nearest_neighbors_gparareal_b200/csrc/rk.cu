@@ -13,8 +13,13 @@
 // multiply-adds in the stage combinations (ulp-level differences, tests: 1e-11 scaled).
 //
 // Layouts: small ODEs (d<=4) one THREAD per slice, everything in registers.  PDE systems one
-// CTA per slice, one thread per grid point, the stage input staged in (double-buffered)
-// shared memory for the neighbour exchange, the k stages in registers, one barrier per stage.
+// CTA per slice, the stage input staged in (double-buffered) shared memory for the neighbour
+// exchange, the k stages in registers, one barrier per stage: rk_pde_kernel with one thread per
+// grid point (any PDE system / normalisation), rk_fhn_tile_kernel with a 2x2 block of points per
+// thread for the FHN target (less shared-memory traffic; bit-identical results).  A long fine
+// step over more than two slices per SM runs as a sequence of balanced launches over
+// (chunk of steps, slice) tasks (launch_fhn_tile_s).  With A.traj set the kernels also store the
+// state after every step (run_F_full).
 #include "common.cuh"
 
 #include <cmath>
