@@ -141,6 +141,13 @@ int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, con
                  int nq, int m, const double* d_theta, const double* d_jitter, double* d_pred,
                  void* stream);
 
+/* Failure rule of the m x m factorisation (models.py:86-92 reach LAPACK potrf, whose failure becomes NaN ->
+ * objective +inf, models.py:250-251): a pivot <= ulps * 2^-52 * K_rr, <= 0 or NaN fails.  Default 1 ulp (the
+ * unbiased match of LAPACK's failure set); 4 = the rule of the first release; values
+ * below 2^-10 are clamped.  Environment override at nngp_create: NNGP_PIVOT_GUARD_ULPS.                  */
+int nngp_set_pivot_guard(nngp_handle_t h, double ulps);
+double nngp_get_pivot_guard(nngp_handle_t h);
+
 /* ---- fused on-device sweep: parareal.py:359-382 for slices i = I..N-1 -------------------
  * per slice: uG_next[i+1] = G(t_i, t_{i+1}, u_next[i]); kNN of u_next[i]; fit+predict;
  * u_next[i+1] = pred + uG_next[i+1].  No host round trip inside; d_starts holds the starts of

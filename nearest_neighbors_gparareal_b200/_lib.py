@@ -56,6 +56,8 @@ SIGNATURES = {
     "nngp_rowwise_maxabs_diff": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "nngp_selftest_math": (ci, [vp, vp, ci, vp, vp, vp, vp]),
     "nngp_launch_count": (cll, [vp]),
+    "nngp_set_pivot_guard": (ci, [vp, cd]),
+    "nngp_get_pivot_guard": (cd, [vp]),
     "nngp_counters": (ci, [vp, c_ll_p, c_ll_p, ci]),
     "nngp_profile_enable": (ci, [vp, ci]),
     "nngp_profile_read": (ci, [vp, vp, vp, ci]),
@@ -291,6 +293,13 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.nngp_launch_count(self.h))
+
+    def set_pivot_guard(self, ulps):
+        """failed-pivot threshold of the GP factorisation in ulps of the diagonal (default 1; round 1 used 4)"""
+        self.check(self.lib.nngp_set_pivot_guard(self.h, float(ulps)))
+
+    def get_pivot_guard(self):
+        return float(self.lib.nngp_get_pivot_guard(self.h))
 
     def counters(self, reset=False):
         """(Nelder-Mead runs, objective evaluations) since the last reset"""

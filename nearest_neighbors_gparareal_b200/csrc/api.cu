@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #define NNGP_QUEUE_SLOTS 4096
@@ -158,6 +159,13 @@ int nngp_create(int device, nngp_handle_t* out) {
     delete h;
     return nngp_fail(nullptr, "cudaMalloc(queues) failed");
   }
+  if (const char* g = getenv("NNGP_PIVOT_GUARD_ULPS")) {
+    if (nngp_set_pivot_guard(h, atof(g)) != 0) {
+      g_create_error = h->err;
+      delete h;
+      return -1;
+    }
+  }
   if (rk_set_tableaus(h) != 0) {
     g_create_error = h->err;
     delete h;
@@ -198,6 +206,16 @@ int nngp_synchronize(nngp_handle_t h, void* stream) {
 }
 
 long long nngp_launch_count(nngp_handle_t h) { return h->launches; }
+
+int nngp_set_pivot_guard(nngp_handle_t h, double ulps) {
+  if (!(ulps == ulps) || ulps < 0.0 || ulps > 1e6) return nngp_fail(h, "set_pivot_guard: ulps=%g outside [0, 1e6]", ulps);
+  // below 2^-10 ulp the running product of the pivots could leave the normal range: "0" means "as small as possible"
+  if (ulps < 9.765625e-4) ulps = 9.765625e-4;
+  h->pivot_guard = ulps * 2.220446049250313e-16;
+  return 0;
+}
+
+double nngp_get_pivot_guard(nngp_handle_t h) { return h->pivot_guard / 2.220446049250313e-16; }
 
 int nngp_counters(nngp_handle_t h, long long* nm_runs, long long* nll_evals, int reset) {
   unsigned long long v[2];

@@ -54,6 +54,8 @@ struct nngp_handle_s {
   void* stage = nullptr;  // device staging for *_host variants
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // a pivot <= pivot_guard * K_rr fails the factorisation (gpfit.cu::gp_head); ulps * 2^-52
+  double pivot_guard = 2.220446049250313e-16;
   // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
   unsigned long long* d_counters = nullptr;
   // task-queue heads of the persistent fit kernel: one zeroed counter per launch

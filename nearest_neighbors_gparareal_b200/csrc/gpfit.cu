@@ -24,9 +24,10 @@
 // order.  The objective is the reference's  0.5 y^T K^-1 y + sum log L_ii + (m/2) log 2 pi  evaluated
 // as 0.5 (sum_k z_k^2 / d_k + log prod_k d_k) with the LDL^T pivots d_k = L_kk^2 and z = L'^-1 y
 // (identical in exact arithmetic; the reference's own optimiser trajectories are not reproducible
-// below 1 ulp of the objective, see DESIGN.md "ties").  A pivot that is <= 4 ulp of the diagonal,
-// <= 0 or NaN fails like LAPACK potf2 and makes the objective +inf exactly as the reference does
-// (NaN -> inf, models.py:250-251).
+// below 1 ulp of the objective, see DESIGN.md "ties").  A pivot that is <= `guard` ulp of the diagonal
+// (default 1 ulp, the threshold at which the failure set agrees with LAPACK's potrf without bias in either
+// direction -- oracle/experiments/pivot_rule_study.py), <= 0 or NaN fails and makes the
+// objective +inf exactly as the reference does on a failed factorisation (NaN -> inf, models.py:250-251).
 #include "common.cuh"
 
 #include <cmath>
@@ -303,7 +304,7 @@ struct GpHead {
   bool fail01;  // pivot 0 or pivot 1 fails: the objective is +inf whatever the rest of the matrix holds
 };
 
-__device__ __forceinline__ GpHead gp_head(double th0, double th1, double jit10, double r2_10, int m) {
+__device__ __forceinline__ GpHead gp_head(double th0, double th1, double jit10, double r2_10, int m, double guard) {
   GpHead g;
   double inv;  // amp = 10**sigma_y, inv = 1/(10**sigma_x)
   exp10_pair(th1, -th0, g.amp, inv);
@@ -320,12 +321,18 @@ __device__ __forceinline__ GpHead gp_head(double th0, double th1, double jit10, 
   double e2[2];
   exp_neg_vec<2>(x2, e2);
   g.dd0 = fma(g.amp_s, e2[1], jit10 * g.sc);  // K'_rr;  K_rr = amp*exp(c*0) + 10**jitter
-  // A pivot that is not above 4 ulp of the diagonal it was subtracted from is rounding noise of an
-  // exactly singular matrix (e.g. identical neighbour rows at a steady state, jitter below one ulp
-  // of the amplitude).  LAPACK's potf2, which only tests pivot <= 0, fails on such matrices because
-  // the cancellation is exact; with fused multiply-adds the residue can stay positive and cascade
-  // (d_k ~ eps^k), which would pass as a "valid" factor with an absurdly small determinant.
-  g.pmin = g.dd0 * 8.8817841970012523e-16;
+  // A pivot that is not above `guard` (= ulps * 2^-52, default 1 ulp) of the diagonal it was subtracted
+  // from is rounding noise of an exactly singular matrix (e.g. identical neighbour rows at a steady
+  // state, jitter below one ulp of the amplitude).  LAPACK's potf2 tests pivot <= 0, but it forms the
+  // pivot as K_jj - (sum of squares): the sum is rounded at ulp(K_jj), so its pivots are multiples of
+  // ulp(K_jj) carrying a few ulp of noise and a singular matrix fails with probability ~1/2 per
+  // duplicated row.  The fused right-looking update below keeps the residue to full relative accuracy:
+  // with a literal "<= 0" test it stays positive and cascades (d_k ~ eps^k), passing as a "valid" factor
+  // with an absurdly small determinant where LAPACK fails.  Measured against np.linalg.cholesky on
+  // steady-state neighbour sets (oracle/experiments/pivot_rule_study.py): at 1 ulp the two failure sets
+  // differ on 1.3 % of the evaluations, evenly in both directions (a literal potf2 restatement differs
+  // from the installed LAPACK on 1-4 %); at 4 ulp (round 1) the device failed 3.3 % more often.
+  g.pmin = g.dd0 * guard;
   // pivots 0 and 1 with exactly the operations of the factorisation in gp_core
   const double k10 = (m > 1) ? g.amp_s * e2[0] : 0.0;
   const double d1 = fma(-(k10 * rcp_pos(g.dd0)), k10, g.dd0);
@@ -341,7 +348,7 @@ struct GpOut {
 template <int M, bool ALPHA>
 __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, const PairSlots<M>& P,
                                          double y, int m, int lane, double* __restrict__ Kt,
-                                         double hml) {
+                                         double hml, double guard) {
   static_assert(M % 2 == 0, "M even: 16-byte loads of column pairs");
   constexpr int LD = Tri<M>::LD;
   constexpr int NP = Tri<M>::NP;
@@ -350,7 +357,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   // FHN target, whose neighbour rows become identical at the steady state, 14 % of the searches and 57 % of
   // the evaluations), and nearly all of those fail at pivot 1: decided by the head alone, before the
   // matrix is built (every lane holds the same values: uniform branch).
-  const GpHead hd = gp_head(th0, th1, jit10, P.r2_10, m);
+  const GpHead hd = gp_head(th0, th1, jit10, P.r2_10, m, guard);
   const double amp = hd.amp, c = hd.c, sc = hd.sc, amp_s = hd.amp_s, dd0 = hd.dd0, pmin = hd.pmin;
   if (!ALPHA) {
     if (__any_sync(FULL, hd.fail01)) {
@@ -559,7 +566,7 @@ __device__ __forceinline__ double shrink_to(double x0, double xj) {
 template <int M>
 __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10, double fatol, double xatol,
                                              const PairSlots<M>& P, double y, int m, int lane,
-                                             double* __restrict__ Lt, double hml, bool head_batch) {
+                                             double* __restrict__ Lt, double hml, bool head_batch, double guard) {
   const int maxfun = 400, maxiter = 400;  // 200 * N
   double sx[3][2], sf[3];
   sx[0][0] = s0; sx[0][1] = s1;
@@ -581,7 +588,7 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
 #pragma unroll
       for (int j = 0; j < 4; j++) hit = hit || (((cmask >> j) & 1u) && p0 == cx0[j] && p1 == cx1[j]);
     }
-    const double f = hit ? dinf() : gp_core<M, false>(p0, p1, jit10, P, y, m, lane, Lt, hml).val;
+    const double f = hit ? dinf() : gp_core<M, false>(p0, p1, jit10, P, y, m, lane, Lt, hml, guard).val;
     fcalls++;
     bool aborted = false, do_shrink = false;
     if (phase == PH_INIT0) {
@@ -682,7 +689,7 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
       const int jl = lane & 3;
       const double t0 = (jl == 0) ? cx0[0] : (jl == 1) ? cx0[1] : (jl == 2) ? cx0[2] : cx0[3];
       const double t1 = (jl == 0) ? cx1[0] : (jl == 1) ? cx1[1] : (jl == 2) ? cx1[2] : cx1[3];
-      cmask = __ballot_sync(FULL, gp_head(t0, t1, jit10, P.r2_10, m).fail01) & 0xFu;
+      cmask = __ballot_sync(FULL, gp_head(t0, t1, jit10, P.r2_10, m, guard).fail01) & 0xFu;
     }
   }
   NMOut o;
@@ -720,12 +727,13 @@ struct FitArgs {
   int j0, dl;             // output dimensions [j0, j0+dl) handled by this launch (a rank's share; dl = d: all)
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
+  double guard;           // failed-pivot threshold relative to the diagonal (ulps * 2^-52)
 };
 
 template <int M>
 __device__ __noinline__ double posterior_mean(double th0, double th1, double jit10, const PairSlots<M>& P,
-                                              double y, double kq, int m, int lane, double* Lt) {
-  const GpOut g = gp_core<M, true>(th0, th1, jit10, P, y, m, lane, Lt, 0.0);
+                                              double y, double kq, int m, int lane, double* Lt, double guard) {
+  const GpOut g = gp_core<M, true>(th0, th1, jit10, P, y, m, lane, Lt, 0.0, guard);
   if (!g.ok) return dnan();
   // K_star = kernel(x, new_x); post_mean = K_star.T @ alph  (models.py:165-167)
   const double ks = g.amp * exp_neg(g.c * kq);
@@ -771,7 +779,7 @@ gp_fit_predict_kernel(FitArgs A) {
     const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
     const signed char* st = A.starts + gtask * 2;
     const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol, P, y, m,
-                                   lane, Lt, hml, A.head_batch != 0);
+                                   lane, Lt, hml, A.head_batch != 0, A.guard);
     unsigned int prior = 0;
     if (lane == 0) {
       A.res[(long long)task * 3] = o.f;
@@ -815,7 +823,7 @@ gp_fit_predict_kernel(FitArgs A) {
     const int ab = best / R;
     const double th0 = rf[3 * best + 1], th1 = rf[3 * best + 2];
     const double kq = (lane < m) ? A.dist[(long long)q * m + lane] : 0.0;
-    double mean = posterior_mean<M>(th0, th1, c_jit10[ab], P, y, kq, m, lane, Lt);
+    double mean = posterior_mean<M>(th0, th1, c_jit10[ab], P, y, kq, m, lane, Lt, A.guard);
     __syncwarp();
     if (lane == 0) {
       A.done[qj] = 0;  // leave the counters clean for the next launch
@@ -836,7 +844,7 @@ gp_fit_predict_kernel(FitArgs A) {
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32)
 gp_nll_kernel(const long long* idx, const double* r2all, const double* Y, int d, int m, int nq, int nt,
-              const double* theta, const double* jitter10, double* out) {
+              const double* theta, const double* jitter10, double* out, double guard) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* Lt = sm + w * (M * (M + 2));
@@ -852,7 +860,7 @@ gp_nll_kernel(const long long* idx, const double* r2all, const double* Y, int d,
   pair_slots_load<M>(P, r2, m);
   for (int t = 0; t < nt; t++) {
     const double v = gp_core<M, false>(theta[(base + t) * 2], theta[(base + t) * 2 + 1], jitter10[base + t], P, y,
-                                       m, lane, Lt, hml).val;
+                                       m, lane, Lt, hml, guard).val;
     if (lane == 0) out[base + t] = v;
   }
 }
@@ -861,7 +869,7 @@ gp_nll_kernel(const long long* idx, const double* r2all, const double* Y, int d,
 template <int M>
 __global__ void __launch_bounds__(GP_WARPS * 32)
 gp_mean_kernel(const long long* idx, const double* dist, const double* r2all, const double* Y, int d,
-               int m, int nq, const double* theta, const double* jitter, double* pred) {
+               int m, int nq, const double* theta, const double* jitter, double* pred, double guard) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* Lt = sm + w * (M * (M + 2));
@@ -876,7 +884,7 @@ gp_mean_kernel(const long long* idx, const double* dist, const double* r2all, co
   pair_slots_init<M>(P, lane, m);
   pair_slots_load<M>(P, r2, m);
   const double mean = posterior_mean<M>(theta[(long long)qj * 2], theta[(long long)qj * 2 + 1], jit10, P, y, kq,
-                                        m, lane, Lt);
+                                        m, lane, Lt, guard);
   if (lane == 0) pred[qj] = mean;
 }
 
@@ -1065,7 +1073,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
-  A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol;
+  A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
   int rc = 0;
   DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   return rc;
@@ -1082,7 +1090,7 @@ static int nll_launch_m(nngp_handle_t h, const long long* idx, const double* r2,
     attr_set = true;
   }
   const int d = h->ds_d;
-  gp_nll_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, r2, h->ds_y, d, m, nq, nt, theta, j10, out);
+  gp_nll_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, r2, h->ds_y, d, m, nq, nt, theta, j10, out, h->pivot_guard);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
@@ -1109,7 +1117,7 @@ static int mean_launch_m(nngp_handle_t h, const long long* idx, const double* di
     attr_set = true;
   }
   const int d = h->ds_d;
-  gp_mean_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, dist, r2, h->ds_y, d, m, nq, theta, jitter, pred);
+  gp_mean_kernel<M><<<(nq * d + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem, st>>>(idx, dist, r2, h->ds_y, d, m, nq, theta, jitter, pred, h->pivot_guard);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;

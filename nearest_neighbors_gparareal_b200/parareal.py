@@ -462,7 +462,8 @@ class PararealDevice(Parareal):
         st['h'].rowwise_maxabs_diff(st['u_next'], st['u_cur'], self.N + 1, self.n, st['err'], st['stream'])
         return st['err'].cpu().numpy()
 
-    def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, max_rows=None, **kwargs):
+    def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, max_rows=None,
+                  iteration_hook=None, **kwargs):
         import torch
         if store_int:
             raise NotImplementedError('intermediate checkpoints are outside the hot path')
@@ -495,6 +496,8 @@ class PararealDevice(Parareal):
                 st['u_cur'].copy_(st['u_next'])
                 break
             err[:, k] = self.device_errors(st)
+            if iteration_hook is not None:  # (k, device state after the sweep of iteration k) -- diagnostics / replay dumps
+                iteration_hook(k, st)
             dt_sweep = time.time() - tic
             sweep_time += dt_sweep
             if st['is_gp']:

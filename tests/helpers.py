@@ -16,11 +16,13 @@ def load_run(name):
 
 def case_system(name):
     """'lorenz_N50_m11' -> (system key, kwargs)"""
-    key = name.split("_")[0]
+    parts = name.split("_")
+    key = parts[0]
+    d = next((int(p[1:]) for p in parts[1:] if p[0] == "d" and p[1:].isdigit()), None)
     if key == "burgers":
-        return "burgers", dict(d_x=32)
+        return "burgers", dict(d_x=d or 32)
     if key == "fhn":
-        return "fhn_pde", dict(d_x=4)
+        return "fhn_pde", dict(d_x=int(round((d / 2) ** 0.5)) if d else 4)  # d = 2 d_x^2
     return key, {}
 
 

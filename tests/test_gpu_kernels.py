@@ -577,3 +577,114 @@ def test_predict_dimension_blocks_equal_full_predict(handle):
         handle.predict_host(q, m, starts, 1, 0.1, 0.1, block=(20, 8))
     with pytest.raises(_lib.NNGPError, match="single query"):
         handle.predict_host(np.concatenate([q, q]), m, np.concatenate([starts, starts]), 1, 0.1, 0.1, block=(0, 8))
+
+
+def _steady_neighbour_sets():
+    """neighbour sets of the steady state of an FHN-PDE run (tests/golden/steady_fhn_d32.npz: rows identical to
+    ~1e-15), plus variants whose first ndup rows are EXACT duplicates -- the regime of the FHN d=512 target from
+    slice ~50 on, where the kernel matrix is singular whenever the jitter is below one ulp of the amplitude"""
+    z = np.load(os.path.join(GOLDEN, "steady_fhn_d32.npz"))
+    x, y, u = z["x"], z["y"], z["u"]
+    m = 20
+    sets = []
+    for qi, ndup in ((40, 1), (60, 1), (80, 1), (50, 2), (50, 3), (70, 5), (70, 10), (90, 20)):
+        idx, _ = onn.knn(u[qi], x, m)
+        xm, ym = x[idx].copy(), y[idx].copy()
+        for t in range(1, ndup):
+            xm[t], ym[t] = xm[0], ym[0]
+        sets.append((xm, ym, ndup))
+    return sets, m
+
+
+def test_failure_set_matches_lapack_in_both_directions(handle):
+    """The objective is +inf where the factorisation fails (models.py:86-92, 250-251).  On nearly singular
+    matrices whether LAPACK's potrf fails is decided by its rounding: a literal potf2 restatement disagrees
+    with the installed LAPACK on 1-4 % of such evaluations (oracle/experiments/pivot_rule_study.py), so the set
+    cannot be reproduced exactly.  The bar: device-inf-where-reference-finite AND reference-inf-where-device-
+    finite are each <= 2 % of the evaluations, neither direction dominates, and outside a band of condition
+    numbers around 1/ulp the two sets are identical."""
+    import torch
+    rng = np.random.default_rng(2)
+    sets, m = _steady_neighbour_sets()
+    dev = torch.device('cuda', handle.device)
+    nt = 120
+    tot = dev_only = ref_only = both_inf = 0
+    for xm, ym, ndup in sets:
+        d = xm.shape[1]
+        handle.dataset_reset()
+        handle.dataset_reserve(m, d)
+        handle.dataset_append_host(xm, ym)
+        idx, dist = handle.knn_host(xm[:1], m)
+        dims = [0, 5, 17]
+        theta = rng.uniform(-8.5, 0.5, (1, d, nt, 2))
+        jit = rng.integers(-20, -11, (1, d, nt)).astype(float)
+        out = torch.empty((1, d, nt), dtype=torch.float64, device=dev)
+        handle.gp_nll(torch.from_numpy(idx).to(dev), 1, m, nt, torch.from_numpy(theta).to(dev),
+                      torch.from_numpy(10.0 ** jit).to(dev), out)
+        got = out.cpu().numpy()[0]
+        r2 = onn.pairwise_sqdist(xm[idx[0]], xm[idx[0]])
+        for j in dims:
+            for t in range(nt):
+                want = onn.neg_log_lik(r2, ym[idx[0], j], theta[0, j, t], jit[0, j, t])
+                g = got[j, t]
+                tot += 1
+                gi, wi = np.isinf(g), np.isinf(want)
+                both_inf += bool(gi and wi)
+                if gi != wi:
+                    dev_only += bool(gi)
+                    ref_only += bool(wi)
+                    # the disagreements sit where the jitter is within a few ulp of the amplitude
+                    amp, jv = 10.0 ** theta[0, j, t, 1], 10.0 ** jit[0, j, t]
+                    assert jv < 64 * 2.2e-16 * amp * m, (theta[0, j, t], jit[0, j, t], g, want)
+    print(f"failure sets: {tot} evaluations, both +inf {both_inf}, device only {dev_only}, reference only {ref_only}")
+    assert both_inf > 0.1 * tot
+    assert dev_only <= 0.02 * tot and ref_only <= 0.02 * tot, (dev_only, ref_only, tot)
+    assert abs(dev_only - ref_only) <= 0.012 * tot, (dev_only, ref_only, tot)
+
+
+def test_nelder_mead_vs_oracle_on_steady_state_neighbours(handle):
+    """the regime that dominates the FHN target (57 % of its evaluations): searches over steady-state neighbour
+    sets, against the ORACLE's Nelder-Mead (SciPy restatement over LAPACK) on the same starts.  Searches that
+    see +inf at every vertex must run the full 400 evaluations in both and return their start point; where the
+    optimiser trajectories agree they agree bit for bit; the selected optimum is as good as the oracle's and the
+    prediction is the oracle's posterior mean at the device's hyper-parameters."""
+    rng = np.random.default_rng(8)
+    sets, m = _steady_neighbour_sets()
+    n_all_inf = n_all_inf_same = n_runs = n_same = n_sel = n_sel_good = 0
+    for xm, ym, ndup in sets[::2] + sets[-1:]:
+        d = xm.shape[1]
+        handle.dataset_reset()
+        handle.dataset_reserve(m, d)
+        handle.dataset_append_host(xm, ym)
+        q = xm[:1] + 0.0
+        starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+        out = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+        idx = out["idx"][0]
+        r2 = onn.pairwise_sqdist(xm[idx], xm[idx])
+        kq = onn.sqdist_rows(q[0], xm[idx])
+        for j in (0, 7, 19, 31):
+            ofv = np.empty(9)
+            for a in range(9):
+                th, fv, ne = onn.nm_run(r2, ym[idx, j], starts[0, j, a, 0].astype(float), onn.JITTERS[a], 0.1, 0.1)
+                ofv[a] = fv
+                n_runs += 1
+                g_th, g_fv, g_ne = out["thetas"][0, j, a, 0], out["fvals"][0, j, a, 0], out["nfev"][0, j, a, 0]
+                if np.isinf(fv) and ne == 400:
+                    n_all_inf += 1
+                    n_all_inf_same += bool(np.isinf(g_fv) and g_ne == 400 and np.array_equal(g_th, th))
+                n_same += bool(np.array_equal(g_th, th) and g_ne == ne)
+            n_sel += 1
+            g_f = out["fval_opt"][0, j]
+            o_f = ofv[onn.select(ofv)]
+            n_sel_good += bool(g_f <= o_f + 0.05 * max(1.0, abs(o_f)))
+            want = onn.posterior_mean(r2, kq, ym[idx, j], out["theta_opt"][0, j], out["jitter_opt"][0, j])
+            if np.isfinite(want):
+                # all rows (nearly) identical: the mean is y * m amp / (m amp + jitter) whatever wins the selection
+                assert abs(out["pred"][0, j] - want) <= 1e-6 * abs(want) + 1e-13, (ndup, j, out["pred"][0, j], want)
+            assert np.isfinite(out["pred"][0, j])
+    print(f"steady state: {n_runs} searches, identical trajectory {n_same}, all-inf (400 evaluations) in the oracle "
+          f"{n_all_inf}, of which identical on the device {n_all_inf_same}; selected optimum as good {n_sel_good}/{n_sel}")
+    assert n_all_inf >= 5
+    assert n_all_inf_same >= 0.9 * n_all_inf
+    assert n_same >= 0.5 * n_runs
+    assert n_sel_good >= 0.9 * n_sel
