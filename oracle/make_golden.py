@@ -209,6 +209,19 @@ def published():
                                     for r in rows if isinstance(r[1], (int, np.integer)) and isinstance(r[6], (int, np.integer))]
     except Exception as e:  # noqa
         res["NNGP_all_but_pend"] = {"error": repr(e)}
+    # Burgers_perf_across_m.py:98-131: rows [N, nn, seed, K, runtime, F_time, mdl_tot_t] of ~100 random seeds x nn = 11..30
+    # (d = N = 128, T = 5 or 5.9 (file name), G = RK1 x 4, F = RK8 x 2000 per slice, '-11' normalisation): the published
+    # distribution of K; stored as [T, nn, seed, K]
+    try:
+        rows = []
+        bdir = os.path.join(REF_DIR, "Burges_nngp_exp_val_speed")
+        for fn in sorted(os.listdir(bdir)):
+            for r in load(os.path.join("Burges_nngp_exp_val_speed", fn)):
+                if len(r) == 7 and int(r[3]) > 0 and int(r[0]) == 128:
+                    rows.append([float(fn.split("_")[-3]), int(r[1]), int(r[2]), int(r[3])])
+        res["Burgers_K_vs_m"] = sorted(rows)
+    except Exception as e:  # noqa
+        res["Burgers_K_vs_m"] = {"error": repr(e)}
     with open(os.path.join(OUT, "published.json"), "w") as fh:
         json.dump(res, fh, indent=0)
     print("published", {k: (v if not isinstance(v, list) else len(v)) for k, v in res.items()

@@ -1,0 +1,87 @@
+"""GPU: the reference's PUBLISHED per-seed convergence counts against the device, run by run.
+
+tests/golden/published.json holds (a) `NNGP_all_but_pend` (Figure_3.py:23-67): 327 runs over FHN-ODE / Roessler /
+Hopf N=32 / Brusselator / Lorenz x nn in {adaptive, 11..16} x eps in {5e-7, 5e-9} x seeds 45..49, and (b)
+`Burgers_K_vs_m` (Burgers_perf_across_m.py): 3875 runs of Burgers d=128, N=128 over nn = 11..30 x ~100 seeds x T in
+{5, 5.9}.  Those runs were made with real JAX arithmetic through the legacy driver, so individual K values are only
+expected to agree where the run is not borderline; the DISTRIBUTION of K_device - K_published is the parity
+statistic (no systematic bias).  usage: published_K_study.py [n_burgers_per_cell] [--ode-only]"""
+import collections
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import nearest_neighbors_gparareal_b200 as nn
+
+pub = json.load(open(os.path.join(ROOT, "tests", "golden", "published.json")))
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n_burg = int(args[0]) if args else 6
+
+ODES = {"fhn_n": (lambda: nn.FHN_ODE(normalization='-11'), {}, 10),
+        "rossler_long_n": (lambda: nn.Rossler(normalization='-11'), {}, 18),
+        "non_aut32_n": (lambda: nn.Hopf(normalization='-11'), dict(N=32), 16),
+        "brus_2d_n": (lambda: nn.Brusselator(normalization='-11'), {}, 24),
+        "lorenz_n": (lambda: nn.Lorenz(normalization='-11'), {}, 17)}
+
+
+def run_ode(name, eps, nnb, R, tol, seed):
+    mk, ckw, e_stop = ODES[name]
+    ode = mk()
+    cfg = nn.Config(ode, **ckw).get()
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+    p = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=eps, verbose='')
+    nnv = nnb if nnb == 'adaptive' else int(nnb)
+    out = p.run(model='nngp', nn=nnv, n_restarts=R, seed=seed, fatol=10 ** tol, xatol=10 ** tol, early_stop=e_stop)
+    return out['k'] if out['converged'] else cfg["N"]
+
+
+def run_burgers(T, nnb, seed):
+    ode = nn.Burgers(d_x=128, normalization='-11')
+    solver = nn.CudaSolverRK(ode.get_vector_field(), Ng=4, Nf=2000, G='RK1', F='RK8')
+    p = nn.PararealDevice(ode, solver, tspan=[0, T], N=128, epsilon=5e-7, verbose='')
+    out = p.run(model='nngp', nn=nnb, seed=seed)
+    return out['k'] if out['converged'] else 128
+
+
+diffs = collections.defaultdict(list)
+t0 = time.time()
+for name, K, eps, nnb, R, tol, seed in pub["NNGP_all_but_pend"]:
+    try:
+        Kd = run_ode(name, eps, nnb, R, tol, seed)
+    except Exception as e:  # noqa
+        print(json.dumps(dict(sys=name, eps=eps, nn=nnb, seed=seed, K_pub=K, error=repr(e)[:200])), flush=True)
+        continue
+    diffs[name].append(Kd - K)
+    print(json.dumps(dict(sys=name, eps=eps, nn=nnb, seed=seed, K_pub=K, K_dev=Kd)), flush=True)
+print("# ODE rows done in %.1fs" % (time.time() - t0), flush=True)
+
+if "--ode-only" not in sys.argv:
+    cells = collections.defaultdict(list)
+    for T, nnb, seed, K in pub["Burgers_K_vs_m"]:
+        cells[(T, nnb)].append((seed, K))
+    for (T, nnb) in sorted(cells):
+        if nnb not in (11, 14, 18, 22, 26, 30):
+            continue
+        for seed, K in cells[(T, nnb)][:n_burg]:
+            t1 = time.time()
+            try:
+                Kd = run_burgers(T, nnb, seed)
+            except Exception as e:  # noqa
+                print(json.dumps(dict(sys="burgers", T=T, nn=nnb, seed=seed, K_pub=K, error=repr(e)[:200])), flush=True)
+                continue
+            diffs[f"burgers_T{T}"].append(Kd - K)
+            print(json.dumps(dict(sys="burgers", T=T, nn=nnb, seed=seed, K_pub=K, K_dev=Kd,
+                                  secs=round(time.time() - t1, 2))), flush=True)
+
+for name, v in diffs.items():
+    v = np.array(v)
+    print("# %-16s n=%3d  mean(K_dev-K_pub)=%+.3f  equal=%d  +1=%d  -1=%d  |d|>=2: %d  hist=%s" % (
+        name, v.size, v.mean(), np.sum(v == 0), np.sum(v == 1), np.sum(v == -1), np.sum(np.abs(v) >= 2),
+        dict(sorted(collections.Counter(v.tolist()).items()))), flush=True)
+allv = np.concatenate([np.array(v) for v in diffs.values()])
+print("# ALL n=%d mean=%+.3f equal=%.1f%% within1=%.1f%%" % (allv.size, allv.mean(), 100 * np.mean(allv == 0),
+                                                          100 * np.mean(np.abs(allv) <= 1)), flush=True)
