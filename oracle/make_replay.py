@@ -21,7 +21,7 @@ from .ref_shim import load_reference
 from . import nngp as onn
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-PICKS = [(2, 8), (2, 40), (2, 120), (2, 400), (3, 6), (3, 30), (3, 80), (3, 250), (3, 500)]
+PICKS = [(2, 4), (2, 8), (2, 14), (2, 22), (2, 40), (2, 120), (2, 400), (3, 5), (3, 6), (3, 10), (3, 18), (3, 30), (3, 80), (3, 500)]
 
 
 class RecordingPool:

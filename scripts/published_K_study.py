@@ -47,6 +47,36 @@ def run_burgers(T, nnb, seed):
     return out['k'] if out['converged'] else 128
 
 
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None   # e.g. rossler_long_n:5e-09
+guards = [float(g) for g in sys.argv[sys.argv.index("--guards") + 1].split(",")] if "--guards" in sys.argv else [None]
+h_mode = sys.argv[sys.argv.index("--h-mode") + 1] if "--h-mode" in sys.argv else "linspace"
+if only:
+    from nearest_neighbors_gparareal_b200 import _lib
+    oname, oeps = only.split(":")
+    for guard in guards:
+        if guard is not None:
+            _lib.default_handle(0).set_pivot_guard(guard)
+        v = []
+        for name, K, eps, nnb, R, tol, seed in pub["NNGP_all_but_pend"]:
+            if name != oname or abs(eps - float(oeps)) > 1e-12:
+                continue
+            mk, ckw, e_stop = ODES[name]
+            ode = mk()
+            cfg = nn.Config(ode, **ckw).get()
+            solver = nn.CudaSolverRK(ode.get_vector_field(), h_mode=h_mode, **cfg)
+            p = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=eps, verbose='')
+            out = p.run(model='nngp', nn=nnb if nnb == 'adaptive' else int(nnb), n_restarts=R, seed=seed,
+                        fatol=10 ** tol, xatol=10 ** tol, early_stop=e_stop + 8)
+            Kd = out['k'] if out['converged'] else 99
+            v.append(Kd - K)
+            print(json.dumps(dict(sys=name, guard=guard, nn=nnb, seed=seed, K_pub=K, K_dev=Kd,
+                                  err_last=float(np.nanmax(out['err'][:, -1])))), flush=True)
+        v = np.array(v)
+        print("# guard %s h_mode %s: n=%d mean=%+.2f median=%+.1f hist=%s" % (
+            guard, h_mode, v.size, v[np.abs(v) < 50].mean(), np.median(v), dict(sorted(collections.Counter(v.tolist()).items()))),
+            flush=True)
+    sys.exit(0)
+
 diffs = collections.defaultdict(list)
 t0 = time.time()
 for name, K, eps, nnb, R, tol, seed in pub["NNGP_all_but_pend"]:

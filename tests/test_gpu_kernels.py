@@ -688,3 +688,43 @@ def test_nelder_mead_vs_oracle_on_steady_state_neighbours(handle):
     assert n_all_inf_same >= 0.9 * n_all_inf
     assert n_same >= 0.5 * n_runs
     assert n_sel_good >= 0.9 * n_sel
+
+
+def _replay_predicts():
+    z = np.load(os.path.join(GOLDEN, "run_fhn_d512_replay.npz"))
+    return z, [{k: z[f"p{p}_{k}"] for k in ("k", "i", "n_rows", "query", "idx", "xm", "ym", "kq", "starts", "preds",
+                                            "thetas", "fvals", "device_pred")} for p in range(int(z["n_predicts"]))]
+
+
+def test_replayed_fhn_d512_predicts_against_the_reference(handle):
+    """Predicts of iterations 3-4 of the FULL-SIZE FHN target (d=512, N=512, m=20; dataset dumped from a device
+    run, tests/golden/run_fhn_d512_replay.npz) replayed through the unmodified reference `NNGP_p.predict`
+    (oracle/make_replay.py).  Same neighbour rows, same host-drawn starts.  Asserted per predict:
+      * searches whose optimum is +inf in the reference (they ran 400 evaluations) are +inf on the device and vice
+        versa, up to 1 % of the searches;
+      * per-search optima: >= 85 % agree to 1e-6 relative in the objective;
+      * the prediction differs from the reference's by <= 5e-8 (a tenth of the Parareal tolerance) in >= 97 % of
+        the output dimensions and by at most the tolerance itself anywhere."""
+    z, preds = _replay_predicts()
+    m, d = int(z["m"]), int(z["d"])
+    for P in preds:
+        handle.dataset_reset()
+        handle.dataset_reserve(m, d)
+        handle.dataset_append_host(P["xm"], P["ym"])
+        out = handle.predict_host(P["query"][None], m, P["starts"][None], 1, 0.1, 0.1, details=True)
+        assert np.array_equal(out["idx"][0], np.arange(m)), "neighbour order (rows are stored in kNN order)"
+        assert np.array_equal(out["dist"][0], P["kq"]) if "dist" in out else True
+        g_f, r_f = out["fvals"][0, :, :, 0], P["fvals"]
+        gi, ri = np.isinf(g_f), np.isinf(r_f)
+        n_s = g_f.size
+        dev_only, ref_only = int(np.sum(gi & ~ri)), int(np.sum(ri & ~gi))
+        fin = ~gi & ~ri
+        close = np.abs(g_f[fin] - r_f[fin]) <= 1e-6 * np.maximum(1.0, np.abs(r_f[fin]))
+        dp = np.abs(out["pred"][0] - P["preds"])
+        print(f"replay k={int(P['k'])} i={int(P['i'])}: searches +inf device-only {dev_only} reference-only {ref_only} "
+              f"of {n_s} (both {int(np.sum(gi & ri))}); optima equal {close.mean():.3f}; |pred - ref| max {dp.max():.2e} "
+              f"median {np.median(dp):.2e}, > 5e-8 in {int(np.sum(dp > 5e-8))} dims; |ref pred| max {np.abs(P['preds']).max():.2e}")
+        assert dev_only <= 0.01 * n_s and ref_only <= 0.01 * n_s, (dev_only, ref_only)
+        assert close.mean() >= 0.85
+        assert np.all(np.isfinite(out["pred"][0]))
+        assert np.mean(dp <= 5e-8) >= 0.97 and dp.max() <= 5e-7, (dp.max(), np.mean(dp <= 5e-8))

@@ -302,3 +302,26 @@ def test_intermediate_checkpoint_and_resume_host_driver(tmp_path):
                                                                 out4['u_last'][i]) for i in range(10)]), rtol=0, atol=0)
     with pytest.raises(Exception, match='do not match'):
         nn.Parareal(nn.Rossler(), NpSolver(), tspan=[0, 1.0], N=10, verbose='').load_int_dump(dump, pool=nn.MyPool())
+
+
+def test_reference_side_binding_derives_from_reference_classes():
+    """integration/cuda_backend.py: the plug-ins are subclasses of the reference's own classes (skipped where the
+    reference is not on the machine); construction needs no GPU"""
+    from integration.ref_env import find_reference
+    if find_reference() is None:
+        pytest.skip("reference modules not on this machine")
+    from integration.cuda_backend import bind
+    B = bind()
+    ref = B.ref
+    ode = B.FHN_PDE(d_x=4)
+    cfg = B.Config(ode, d_x=4).get()
+    solver = B.CudaSolverRK(ode.get_vector_field(), **cfg)
+    model = B.CudaNNGP(n=ode.get_dim(), N=cfg["N"], worker_pool=None, nn=12, seed=45)
+    par = B.CudaParareal(ode, solver, **cfg)     # parareal.py:37-41 type checks pass
+    assert isinstance(ode, ref.systems.FHN_PDE) and isinstance(solver, ref.solver.SolverRK)
+    assert isinstance(model, ref.models.NNGP_p) and isinstance(par, ref.parareal.Parareal)
+    assert type(par)._parareal is ref.parareal.Parareal._parareal
+    assert model.fatol == 0.1 and model.nn == 12 and model.name == 'NNGP'
+    assert np.array_equal(ode.get_init_cond(), nn.FHN_PDE(d_x=4).get_init_cond())
+    with pytest.raises(Exception, match="instance of the ODE class"):
+        ref.parareal.Parareal(object(), solver, **cfg)
