@@ -34,7 +34,8 @@ def _stale(target, sources):
 def build(force=False, verbose=False):
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "nngpara.h")]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "nngpara.h"))
     objs = []
     procs = []
     for src, extra in UNITS:

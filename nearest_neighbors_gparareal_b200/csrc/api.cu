@@ -145,12 +145,14 @@ int nngp_create(int device, nngp_handle_t* out) {
     return nngp_fail(nullptr, "nngp_create: device sm_%d%d is not Blackwell sm_100a", prop.major, prop.minor);
   nngp_handle_t h = new nngp_handle_s();
   h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->fit_legacy = getenv("NNGP_FIT_LEGACY") != nullptr;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "cudaStreamCreate failed");
   }
-  if (cudaMalloc(&h->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMemset(h->d_counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "cudaMalloc(counters) failed");
   }
@@ -218,9 +220,12 @@ int nngp_set_pivot_guard(nngp_handle_t h, double ulps) {
 double nngp_get_pivot_guard(nngp_handle_t h) { return h->pivot_guard / 2.220446049250313e-16; }
 
 int nngp_counters(nngp_handle_t h, long long* nm_runs, long long* nll_evals, int reset) {
-  unsigned long long v[2];
+  unsigned long long v[8];
   NNGP_CUDA(h, cudaDeviceSynchronize());
   NNGP_CUDA(h, cudaMemcpy(v, h->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+  if (getenv("NNGP_FIT_STATS"))
+    fprintf(stderr, "fit stats: searches %llu evals %llu | warp-rounds %llu wanted group-evals %llu busy group-slots %llu "
+            "fast-forwarded iterations %llu max rounds of a warp (all launches) %llu\n", v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
   if (nm_runs) *nm_runs = (long long)v[0];
   if (nll_evals) *nll_evals = (long long)v[1];
   if (reset) NNGP_CUDA(h, cudaMemset(h->d_counters, 0, sizeof(v)));

@@ -56,6 +56,14 @@ struct nngp_handle_s {
   cudaStream_t own_stream = nullptr;
   // a pivot <= pivot_guard * K_rr fails the factorisation (gpfit.cu::gp_head); ulps * 2^-52
   double pivot_guard = 2.220446049250313e-16;
+  // per-handle (= per-device) launch state of the GP kernels, indexed by M/2: resident CTAs per SM and
+  // "dynamic shared memory attribute set" flags (cudaFuncSetAttribute is per device)
+  int sm_count = 148;
+  int occ_fit[17] = {0};
+  int occ_fit_grouped[17] = {0};
+  bool attr_nll[17] = {false};
+  bool attr_mean[17] = {false};
+  bool fit_legacy = false;  // NNGP_FIT_LEGACY=1: one search per warp (round-1 kernel), kept for A/B runs
   // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
   unsigned long long* d_counters = nullptr;
   // task-queue heads of the persistent fit kernel: one zeroed counter per launch

@@ -740,6 +740,8 @@ __device__ __noinline__ double posterior_mean(double th0, double th1, double jit
   return warp_sum((lane < m) ? ks * g.val : 0.0);
 }
 
+#include "gpfit_group.cuh"
+
 // registers per thread: 4-warp CTAs, K CTAs per SM
 #ifndef FIT_OCC20
 #define FIT_OCC20 3
@@ -1014,7 +1016,7 @@ static size_t warp_tile_bytes() { return sizeof(double) * (size_t)GP_WARPS * M *
 
 template <int M>
 static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
-  static int ctas_per_sm = 0;
+  int& ctas_per_sm = h->occ_fit[M / 2];
   const size_t smem = warp_tile_bytes<M>();
   if (ctas_per_sm == 0) {
     NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_predict_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1022,8 +1024,7 @@ static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
                                                                GP_WARPS * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int sms = h->sm_count;
   // persistent grid: every resident warp slot pulls searches from the queue
   long long blocks = (long long)sms * ctas_per_sm;
   const long long need = (A.ntasks + GP_WARPS - 1) / GP_WARPS;
@@ -1031,6 +1032,30 @@ static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
   ProfScope prof(h, 3, st);
   gp_fit_predict_kernel<M><<<(unsigned)blocks, GP_WARPS * 32, smem, st>>>(A);
   h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// grouped searches (gpfit_group.cuh) + selection / mean kernel
+template <int M>
+static int fit_grouped_launch_m(nngp_handle_t h, const FitArgs& A, int nqj, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)GP_WARPS * Grp<M>::PER_WARP;
+  const size_t smem2 = warp_tile_bytes<M>();
+  int& occ = h->occ_fit_grouped[M / 2];
+  if (occ == 0) {
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_grouped_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_select_mean_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    NNGP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gp_fit_grouped_kernel<M>, GP_WARPS * 32, smem));
+    if (occ < 1) occ = 1;
+  }
+  long long blocks = (long long)h->sm_count * occ;
+  const long long per_cta = GP_WARPS * Grp<M>::NG;
+  const long long need = (A.ntasks + per_cta - 1) / per_cta;
+  if (blocks > need) blocks = need;
+  ProfScope prof(h, 3, st);
+  gp_fit_grouped_kernel<M><<<(unsigned)blocks, GP_WARPS * 32, smem, st>>>(A);
+  gp_select_mean_kernel<M><<<(nqj + GP_WARPS - 1) / GP_WARPS, GP_WARPS * 32, smem2, st>>>(A, nqj);
+  h->launches += 2;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1075,7 +1100,12 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
   A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
   int rc = 0;
-  DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
+  if (h->fit_legacy) {
+    DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
+  } else {
+    const int nqj = nq * dl;
+    DISPATCH_M(m, rc = fit_grouped_launch_m<MM>(h, A, nqj, st));
+  }
   return rc;
 }
 
@@ -1084,7 +1114,7 @@ static int nll_launch_m(nngp_handle_t h, const long long* idx, const double* r2,
                         int nt, const double* theta, const double* j10, double* out,
                         cudaStream_t st) {
   const size_t smem = warp_tile_bytes<M>();
-  static bool attr_set = false;
+  bool& attr_set = h->attr_nll[M / 2];
   if (!attr_set) {
     NNGP_CUDA(h, cudaFuncSetAttribute(gp_nll_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -1111,7 +1141,7 @@ static int mean_launch_m(nngp_handle_t h, const long long* idx, const double* di
                          const double* r2, int nq, int m, const double* theta,
                          const double* jitter, double* pred, cudaStream_t st) {
   const size_t smem = warp_tile_bytes<M>();
-  static bool attr_set = false;
+  bool& attr_set = h->attr_mean[M / 2];
   if (!attr_set) {
     NNGP_CUDA(h, cudaFuncSetAttribute(gp_mean_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -1132,3 +1162,16 @@ int gp_mean_launch(nngp_handle_t h, const long long* d_idx, const double* d_dist
   DISPATCH_M(m, rc = mean_launch_m<MM>(h, d_idx, d_dist, d_r2, nq, m, d_theta, d_jitter, d_pred, st));
   return rc;
 }
+
+#ifdef NNGP_FIT_STATS
+extern "C" void nngp_fit_stats_dump(void) {
+  unsigned long long hst[18];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(hst, g_fail_hist, sizeof(hst));
+  fprintf(stderr, "first failing pivot of wanted evaluations:");
+  for (int k = 0; k < 16; k++) fprintf(stderr, " %d:%llu", k, hst[k]);
+  fprintf(stderr, " | head fail01 %llu of wanted %llu\n", hst[16], hst[17]);
+  unsigned long long z[18] = {0};
+  cudaMemcpyToSymbol(g_fail_hist, z, sizeof(z));
+}
+#endif

@@ -18,8 +18,7 @@ import numpy as np
 import nearest_neighbors_gparareal_b200 as nn
 
 pub = json.load(open(os.path.join(ROOT, "tests", "golden", "published.json")))
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
-n_burg = int(args[0]) if args else 6
+n_burg = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 6
 
 ODES = {"fhn_n": (lambda: nn.FHN_ODE(normalization='-11'), {}, 10),
         "rossler_long_n": (lambda: nn.Rossler(normalization='-11'), {}, 18),
