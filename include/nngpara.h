@@ -147,6 +147,10 @@ int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, con
  * below 2^-10 are clamped.  Environment override at nngp_create: NNGP_PIVOT_GUARD_ULPS.                  */
 int nngp_set_pivot_guard(nngp_handle_t h, double ulps);
 double nngp_get_pivot_guard(nngp_handle_t h);
+/* Which search kernel nngp_fit_predict / nngp_predict_host / nngp_sweep launch: 0 auto (default), 1 one Nelder-Mead
+ * search per warp, 2 several searches per warp (32 / (m/2)).  Results are bit-identical; only the speed differs
+ * (DESIGN.md section 4.5).  Environment override at nngp_create: NNGP_FIT_MODE=auto|warp|grouped.              */
+int nngp_set_fit_mode(nngp_handle_t h, int mode);
 
 /* ---- fused on-device sweep: parareal.py:359-382 for slices i = I..N-1 -------------------
  * per slice: uG_next[i+1] = G(t_i, t_{i+1}, u_next[i]); kNN of u_next[i]; fit+predict;

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nngp_launch_count": (cll, [vp]),
     "nngp_set_pivot_guard": (ci, [vp, cd]),
     "nngp_get_pivot_guard": (cd, [vp]),
+    "nngp_set_fit_mode": (ci, [vp, ci]),
     "nngp_counters": (ci, [vp, c_ll_p, c_ll_p, ci]),
     "nngp_profile_enable": (ci, [vp, ci]),
     "nngp_profile_read": (ci, [vp, vp, vp, ci]),
@@ -297,6 +298,10 @@ class Handle:
     def set_pivot_guard(self, ulps):
         """failed-pivot threshold of the GP factorisation in ulps of the diagonal (default 1; round 1 used 4)"""
         self.check(self.lib.nngp_set_pivot_guard(self.h, float(ulps)))
+
+    def set_fit_mode(self, mode):
+        """'auto' | 'warp' (one search per warp) | 'grouped' (several searches per warp); same bits either way"""
+        self.check(self.lib.nngp_set_fit_mode(self.h, {"auto": 0, "warp": 1, "grouped": 2}[mode]))
 
     def get_pivot_guard(self):
         return float(self.lib.nngp_get_pivot_guard(self.h))

@@ -146,7 +146,8 @@ int nngp_create(int device, nngp_handle_t* out) {
   nngp_handle_t h = new nngp_handle_s();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  h->fit_legacy = getenv("NNGP_FIT_LEGACY") != nullptr;
+  if (const char* fm = getenv("NNGP_FIT_MODE")) h->fit_mode = (strcmp(fm, "warp") == 0) ? 1 : (strcmp(fm, "grouped") == 0) ? 2 : 0;
+  if (getenv("NNGP_FIT_LEGACY")) h->fit_mode = 1;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "cudaStreamCreate failed");
@@ -155,6 +156,14 @@ int nngp_create(int device, nngp_handle_t* out) {
       cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "cudaMalloc(counters) failed");
+  }
+  if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&h->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) {
+    delete h;
+    return nngp_fail(nullptr, "nngp_create: auxiliary stream / events failed");
   }
   if (cudaMalloc(&h->d_queues, NNGP_QUEUE_SLOTS * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(h->d_queues, 0, NNGP_QUEUE_SLOTS * sizeof(unsigned int)) != cudaSuccess) {
@@ -192,6 +201,10 @@ int nngp_destroy(nngp_handle_t h) {
   if (h->stage) cudaFree(h->stage);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->d_ticket) cudaFree(h->d_ticket);
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_queues) cudaFree(h->d_queues);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -214,6 +227,12 @@ int nngp_set_pivot_guard(nngp_handle_t h, double ulps) {
   // below 2^-10 ulp the running product of the pivots could leave the normal range: "0" means "as small as possible"
   if (ulps < 9.765625e-4) ulps = 9.765625e-4;
   h->pivot_guard = ulps * 2.220446049250313e-16;
+  return 0;
+}
+
+int nngp_set_fit_mode(nngp_handle_t h, int mode) {
+  if (mode < 0 || mode > 2) return nngp_fail(h, "set_fit_mode: mode=%d outside {0 auto, 1 warp, 2 grouped}", mode);
+  h->fit_mode = mode;
   return 0;
 }
 
@@ -616,6 +635,30 @@ int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, lon
   return 0;
 }
 
+// Everything of a slice that precedes the fits: the coarse step uG_next[i+1] = G(u_next[i]) on the auxiliary stream,
+// beside it ONE launch for distance scan + top-m + neighbour matrix (general shapes: three launches); the caller's
+// stream joins the auxiliary one before the fit, whose epilogue adds uG_next[i+1] to the prediction.
+static int sweep_slice_prologue(nngp_handle_t h, const SystemDesc& s, int method_g, int h_mode, long long steps_g,
+                                const double* d_ti, double* ui, double* gn, int d, int m, long long n, long long* idx,
+                                double* dist, void* kws, void* fws, cudaStream_t st) {
+  const bool fork = getenv("NNGP_SWEEP_NO_FORK") == nullptr;
+  cudaStream_t sg = fork ? h->aux_stream : st;
+  if (fork) {
+    NNGP_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    NNGP_CUDA(h, cudaStreamWaitEvent(sg, h->ev_fork, 0));
+  }
+  if (int rc = rk_launch(h, s, method_g, h_mode, steps_g, 1, d_ti, d_ti + 1, ui, d, gn, d, sg)) return rc;
+  if (fork) NNGP_CUDA(h, cudaEventRecord(h->ev_join, sg));
+  if (knn_prep_fused_ok(h, n, m) && getenv("NNGP_SWEEP_NO_FUSED_PROLOGUE") == nullptr) {
+    if (int rc = knn_prep_fused_launch(h, ui, m, n, idx, dist, (double*)fws, kws, h->d_ticket, st)) return rc;
+  } else {
+    if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
+    if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
+  }
+  if (fork) NNGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+  return 0;
+}
+
 // ---- fused on-device sweep (parareal.py:359-382) --------------------------------------
 int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long steps_g,
                const double* d_t, int N, int I, int m, int n_restarts,
@@ -648,9 +691,7 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
     double* ui = d_u_next + (long long)i * d;
     double* un = d_u_next + (long long)(i + 1) * d;
     double* gn = d_uG_next + (long long)(i + 1) * d;
-    if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
-    if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
-    if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
+    if (int rc = sweep_slice_prologue(h, *s, method_g, h_mode, steps_g, d_t + i, ui, gn, d, m, n, idx, dist, kws, fws, st)) return rc;
     if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), order + (size_t)(i - I) * seg_len, 1, m,
                                        n_restarts, d_starts + (size_t)(i - I) * per_predict, fatol, xatol, un, gn, d,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st))
@@ -696,9 +737,7 @@ int nngp_sweep_shard(nngp_handle_t h, int sys, int method_g, int h_mode, long lo
     double* un = d_u_next + (long long)(i + 1) * d;
     double* gn = d_uG_next + (long long)(i + 1) * d;
     const signed char* starts_i = d_starts + (size_t)(i - I) * per_predict;
-    if (int rc = rk_launch(h, *s, method_g, h_mode, steps_g, 1, d_t + i, d_t + i + 1, ui, d, gn, d, st)) return rc;
-    if (int rc = knn_launch(h, ui, 1, m, n, idx, dist, kws, st)) return rc;
-    if (int rc = gp_prep_launch(h, idx, 1, m, (double*)fws, st)) return rc;
+    if (int rc = sweep_slice_prologue(h, *s, method_g, h_mode, steps_g, d_t + i, ui, gn, d, m, n, idx, dist, kws, fws, st)) return rc;
     if (int rc = gp_order_launch(h, starts_i + (size_t)j0 * nruns * 2, 1, seg_len, 0, order, st)) return rc;
     if (int rc = gp_fit_predict_launch(h, idx, dist, fws, next_queue(h, st), order, 1, m, n_restarts, starts_i, fatol,
                                        xatol, un, gn, d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, j0, dl))

@@ -54,6 +54,10 @@ struct nngp_handle_s {
   void* stage = nullptr;  // device staging for *_host variants
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // sweep: the coarse step of a slice runs on aux_stream beside the neighbour search (fork / join with two events)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  unsigned int* d_ticket = nullptr;  // last-CTA-done counter of the fused sweep prologue (zero between launches)
   // a pivot <= pivot_guard * K_rr fails the factorisation (gpfit.cu::gp_head); ulps * 2^-52
   double pivot_guard = 2.220446049250313e-16;
   // per-handle (= per-device) launch state of the GP kernels, indexed by M/2: resident CTAs per SM and
@@ -63,7 +67,10 @@ struct nngp_handle_s {
   int occ_fit_grouped[17] = {0};
   bool attr_nll[17] = {false};
   bool attr_mean[17] = {false};
-  bool fit_legacy = false;  // NNGP_FIT_LEGACY=1: one search per warp (round-1 kernel), kept for A/B runs
+  // which search kernel a fit launches: 0 auto (several searches per warp for batched queries with m <= 20, where it
+  // is 1.4-4x faster; one search per warp for the serial sweep, whose searches fail early and cheaply 45 % of the
+  // time -- DESIGN.md section 4.5), 1 always one search per warp, 2 always grouped.  NNGP_FIT_MODE=auto|warp|grouped
+  int fit_mode = 0;
   // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
   unsigned long long* d_counters = nullptr;
   // task-queue heads of the persistent fit kernel: one zeroed counter per launch
@@ -114,6 +121,9 @@ void rk_host_tableau(int method, int* S, double* a, double* b, double* c);
 size_t knn_workspace_bytes(int nq, long long n, int m);
 int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
                long long* d_idx, double* d_dist, void* ws, cudaStream_t st);
+bool knn_prep_fused_ok(nngp_handle_t h, long long n, int m);
+int knn_prep_fused_launch(nngp_handle_t h, const double* d_q, int m, long long n, long long* d_idx, double* d_dist,
+                          double* d_r2, void* ws, unsigned int* ticket, cudaStream_t st);
 int dataset_append_launch(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
                           cudaStream_t st);
 int append_iteration_launch(nngp_handle_t h, const double* d_u_cur, const double* d_uF,

@@ -1100,7 +1100,8 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
   A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
   int rc = 0;
-  if (h->fit_legacy) {
+  const bool grouped = (h->fit_mode == 2) || (h->fit_mode == 0 && nq >= 4 && m <= 20);
+  if (!grouped) {
     DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   } else {
     const int nqj = nq * dl;

@@ -324,7 +324,7 @@ __device__ __forceinline__ bool nm_step(NMState& S, double f, double fatol, doub
 }
 
 #ifndef GRP_OCC20
-#define GRP_OCC20 3
+#define GRP_OCC20 2
 #endif
 template <int M> struct GrpOcc { static constexpr int value = (M <= 12) ? 4 : ((M <= 20) ? GRP_OCC20 : 2); };
 

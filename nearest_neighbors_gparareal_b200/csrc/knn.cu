@@ -278,17 +278,12 @@ __device__ __forceinline__ void warp_merge32(double& d, long long& i, double bd,
 // Every warp keeps a sorted list of its m best over the lanes.  A round of 32 candidates is tested against the
 // list's m-th key; a few survivors are inserted one by one (ballot + shuffle), many (the first rounds) are
 // sorted by a bitonic network and merged.  Warp 0 then merges the warps' lists.
-__global__ void __launch_bounds__(KNN_SEL_THREADS)
-select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_idx, long long n,
-              long long chunk, int m, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
-  constexpr int NW = KNN_SEL_THREADS / 32;
-  __shared__ double cd[NW * 32];
-  __shared__ long long ci[NW * 32];
-  const int q = blockIdx.y;
+template <int NW>
+__device__ __forceinline__ void select_topm_cta(const double* __restrict__ dq, const long long* __restrict__ iq,
+                                                long long lo, long long hi, int m, long long* __restrict__ idx_out,
+                                                double* __restrict__ dist_out, double* cd, long long* ci) {
+  constexpr int NT = NW * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const double* dq = dist + (long long)q * n;
-  const long long* iq = in_idx ? in_idx + (long long)q * n : nullptr;
-  const long long lo = (long long)blockIdx.x * chunk, hi = min(n, lo + chunk);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const long long IMAX = 0x7fffffffffffffffLL;
   // lane l holds the l-th smallest key seen by this warp (l < m), padding beyond
@@ -300,19 +295,19 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
   {
     const long long i0 = lo + (long long)w * 32 + lane;
     if (i0 < hi) {
-      cn = dq[i0];
+      cn = __ldcg(dq + i0);
       cnidx = iq ? iq[i0] : i0;
     }
   }
-  for (long long base = lo + (long long)w * 32; base < hi; base += KNN_SEL_THREADS) {
+  for (long long base = lo + (long long)w * 32; base < hi; base += NT) {
     double c = cn;
     long long cidx = cnidx;
     {
-      const long long i1 = base + KNN_SEL_THREADS + lane;
+      const long long i1 = base + NT + lane;
       cn = INF;
       cnidx = IMAX;
       if (i1 < hi) {
-        cn = dq[i1];
+        cn = __ldcg(dq + i1);
         cnidx = iq ? iq[i1] : i1;
       }
     }
@@ -371,11 +366,132 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
     }
   }
   if (lane < m) {
-    const long long ob = ((long long)q * gridDim.x + blockIdx.x) * m;
-    idx_out[ob + lane] = bi;
-    dist_out[ob + lane] = (bi == IMAX) ? INF : bd;
+    idx_out[lane] = bi;
+    dist_out[lane] = (bi == IMAX) ? INF : bd;
   }
 }
+
+__global__ void __launch_bounds__(KNN_SEL_THREADS)
+select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_idx, long long n,
+              long long chunk, int m, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
+  constexpr int NW = KNN_SEL_THREADS / 32;
+  __shared__ double cd[NW * 32];
+  __shared__ long long ci[NW * 32];
+  const int q = blockIdx.y;
+  const double* dq = dist + (long long)q * n;
+  const long long* iq = in_idx ? in_idx + (long long)q * n : nullptr;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(n, lo + chunk);
+  const long long ob = ((long long)q * gridDim.x + blockIdx.x) * m;
+  select_topm_cta<NW>(dq, iq, lo, hi, m, idx_out + ob, dist_out + ob, cd, ci);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sweep prologue of one slice in ONE launch (was: distance scan, selection, neighbour matrix = three
+// dependent launches of 35 + 24 + 26 us): every CTA scans 128 dataset rows for the single query; the CTA that
+// finishes last (ticket counter) selects the m nearest rows over all distances and forms the m x m matrix of
+// squared distances between them (the r2 of the GP kernels, cdist arithmetic).  n <= KNN_CHUNK rows.
+// ---------------------------------------------------------------------------------------
+static constexpr int PRO_THREADS = 128;
+static constexpr int PRO_JC = 64;
+
+template <int PF>
+__global__ void __launch_bounds__(PRO_THREADS)
+sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ X, long long cap, long long n, int d,
+                      const double* __restrict__ q, int m, double* __restrict__ dist_all, unsigned int* ticket,
+                      long long* __restrict__ idx_out, double* __restrict__ dist_out, double* __restrict__ r2) {
+  extern __shared__ double qs[];  // [d]
+  constexpr int NW = PRO_THREADS / 32;
+  __shared__ double cd[NW * 32];
+  __shared__ long long ci[NW * 32];
+  __shared__ double tile[NNGP_MAX_NEIGHBOURS][PRO_JC + 1];
+  __shared__ bool last;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) qs[e] = q[e];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double* xp = XT + i;
+    double acc = 0.0;
+    double cur[PF], nxt[PF];
+    const int nb = d / PF;
+#pragma unroll
+    for (int u = 0; u < PF; u++) cur[u] = (nb > 0) ? xp[(long long)u * cap] : 0.0;
+    for (int b = 0; b < nb; b++) {
+      const int j0 = b * PF;
+      if (b + 1 < nb) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) nxt[u] = xp[(long long)(j0 + PF + u) * cap];
+      }
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        const double diff = qs[j0 + u] - cur[u];
+        acc = acc + diff * diff;
+      }
+#pragma unroll
+      for (int u = 0; u < PF; u++) cur[u] = nxt[u];
+    }
+    for (int j = nb * PF; j < d; j++) {
+      const double diff = qs[j] - xp[(long long)j * cap];
+      acc = acc + diff * diff;
+    }
+    __stcg(dist_all + i, acc);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  select_topm_cta<NW>(dist_all, nullptr, 0, n, m, idx_out, dist_out, cd, ci);
+  __syncthreads();  // idx_out written by warp 0 of this CTA
+  // neighbour matrix: r2[a][b] = ||x_a - x_b||^2, strict left-to-right sums
+  const int npairs = m * (m + 1) / 2;
+  constexpr int PP = (NNGP_MAX_NEIGHBOURS * (NNGP_MAX_NEIGHBOURS + 1) / 2 + PRO_THREADS - 1) / PRO_THREADS;
+  int pa[PP], pb[PP];
+  double acc2[PP];
+#pragma unroll
+  for (int u = 0; u < PP; u++) {
+    const int pidx = threadIdx.x + u * PRO_THREADS;
+    int a = 0, b = 0;
+    if (pidx < npairs) {
+      a = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= pidx) a++;
+      while (a * (a + 1) / 2 > pidx) a--;
+      b = pidx - a * (a + 1) / 2;
+    }
+    pa[u] = a;
+    pb[u] = b;
+    acc2[u] = 0.0;
+  }
+  for (int j0 = 0; j0 < d; j0 += PRO_JC) {
+    const int jn = min(PRO_JC, d - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * PRO_JC; e += PRO_THREADS) {
+      const int r = e / PRO_JC, jj = e - r * PRO_JC;
+      if (jj < jn) tile[r][jj] = X[__ldcg(idx_out + r) * d + j0 + jj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PP; u++) {
+      if (threadIdx.x + u * PRO_THREADS < npairs) {
+        double sacc = acc2[u];
+        for (int jj = 0; jj < jn; jj++) {
+          const double diff = tile[pa[u]][jj] - tile[pb[u]][jj];
+          sacc = sacc + diff * diff;
+        }
+        acc2[u] = sacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PP; u++) {
+    if (threadIdx.x + u * PRO_THREADS < npairs) {
+      r2[pa[u] * m + pb[u]] = acc2[u];
+      r2[pb[u] * m + pa[u]] = acc2[u];
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch
+}
+
 
 static constexpr long long KNN_CHUNK = 4096;  // rows up to which one CTA selects alone; chunks are >= a quarter of it
 
@@ -443,6 +559,24 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
     select_kernel<<<dim3(1, nq), KNN_SEL_THREADS, 0, st>>>(cand_d, cand_i, nc, nc, m, d_idx, d_dist);
     h->launches += 2;
   }
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// scan + selection + neighbour matrix of ONE query in one launch; false when the shape needs the general path
+bool knn_prep_fused_ok(nngp_handle_t h, long long n, int m) {
+  return n <= KNN_CHUNK && n >= m && (size_t)h->ds_d * sizeof(double) <= 48 * 1024;
+}
+
+int knn_prep_fused_launch(nngp_handle_t h, const double* d_q, int m, long long n, long long* d_idx, double* d_dist,
+                          double* d_r2, void* ws, unsigned int* ticket, cudaStream_t st) {
+  const int d = h->ds_d;
+  double* dist = (double*)ws;
+  ProfScope prof(h, 1, st);
+  const unsigned g = (unsigned)((n + PRO_THREADS - 1) / PRO_THREADS);
+  sweep_prologue_kernel<16><<<g, PRO_THREADS, (size_t)d * sizeof(double), st>>>(h->ds_xt, h->ds_x, h->ds_cap, n, d, d_q, m,
+                                                                             dist, ticket, d_idx, d_dist, d_r2);
+  h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
 }
