@@ -94,6 +94,8 @@ int nngp_get_tableau(int method, int* stages, double* a, double* b, double* c);
 /* ---- dataset: x / D of parareal.py:336-339, held on the device ------------------------ */
 int nngp_dataset_reserve(nngp_handle_t h, long long cap_rows, int d);
 int nngp_dataset_reset(nngp_handle_t h);
+/* keep only the first `rows` rows (a resumed / replayed iteration appends its rows again) */
+int nngp_dataset_truncate(nngp_handle_t h, long long rows);
 int nngp_dataset_append(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
                         void* stream);
 int nngp_dataset_append_host(nngp_handle_t h, const double* x, const double* y, long long rows);

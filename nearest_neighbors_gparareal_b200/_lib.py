@@ -39,6 +39,7 @@ SIGNATURES = {
     "nngp_get_tableau": (ci, [ci, c_int_p, vp, vp, vp]),
     "nngp_dataset_reserve": (ci, [vp, cll, ci]),
     "nngp_dataset_reset": (ci, [vp]),
+    "nngp_dataset_truncate": (ci, [vp, cll]),
     "nngp_dataset_append": (ci, [vp, vp, vp, cll, vp]),
     "nngp_dataset_append_host": (ci, [vp, vp, vp, cll]),
     "nngp_dataset_rows": (cll, [vp]),
@@ -291,6 +292,9 @@ class Handle:
 
     def synchronize(self, stream=None):
         self.check(self.lib.nngp_synchronize(self.h, stream))
+
+    def dataset_truncate(self, rows):
+        self.check(self.lib.nngp_dataset_truncate(self.h, int(rows)))
 
     def launch_count(self):
         return int(self.lib.nngp_launch_count(self.h))

@@ -442,6 +442,12 @@ int nngp_dataset_reset(nngp_handle_t h) {
   return 0;
 }
 
+int nngp_dataset_truncate(nngp_handle_t h, long long rows) {
+  if (rows < 0 || rows > h->ds_rows) return nngp_fail(h, "dataset_truncate: rows=%lld outside [0,%lld]", rows, h->ds_rows);
+  h->ds_rows = rows;
+  return 0;
+}
+
 long long nngp_dataset_rows(nngp_handle_t h) { return h->ds_rows; }
 int nngp_dataset_dim(nngp_handle_t h) { return h->ds_d; }
 

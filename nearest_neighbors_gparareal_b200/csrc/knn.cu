@@ -387,11 +387,11 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
 
 // ---------------------------------------------------------------------------------------
 // Sweep prologue of one slice in ONE launch (was: distance scan, selection, neighbour matrix = three
-// dependent launches of 35 + 24 + 26 us): every CTA scans 128 dataset rows for the single query; the CTA that
+// dependent launches of 35 + 24 + 26 us): every CTA scans 256 dataset rows for the single query; the CTA that
 // finishes last (ticket counter) selects the m nearest rows over all distances and forms the m x m matrix of
 // squared distances between them (the r2 of the GP kernels, cdist arithmetic).  n <= KNN_CHUNK rows.
 // ---------------------------------------------------------------------------------------
-static constexpr int PRO_THREADS = 128;
+static constexpr int PRO_THREADS = 256;
 static constexpr int PRO_JC = 64;
 
 template <int PF>

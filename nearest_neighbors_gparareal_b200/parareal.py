@@ -462,6 +462,21 @@ class PararealDevice(Parareal):
         st['h'].rowwise_maxabs_diff(st['u_next'], st['u_cur'], self.N + 1, self.n, st['err'], st['stream'])
         return st['err'].cpu().numpy()
 
+    def device_advance(self, st, err_k):
+        """parareal.py:402-416 after a sweep: the new iterate becomes the current one, `I` moves over the slices whose
+        error is below epsilon.  err_k = the per-slice errors of this iteration (host array); returns the new I."""
+        I = st['I']
+        err_k[I] = 0
+        st['u_cur'].copy_(st['u_next'])
+        st['uG_cur'].copy_(st['uG_next'])
+        for p in range(I + 1, self.N + 1):
+            if err_k[p] < self.epsilon:
+                I += 1
+            else:
+                break
+        st['I'] = I
+        return I
+
     def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, max_rows=None,
                   iteration_hook=None, **kwargs):
         import torch
@@ -506,15 +521,7 @@ class PararealDevice(Parareal):
                 model.tot_train_t += dt_sweep
             if np.any(np.isnan(err[:, k])) and bool(torch.isnan(st['uG_next']).any()):
                 raise Exception("NaN values in initial coarse solve - increase Ng!")
-            err[I, k] = 0
-            st['u_cur'].copy_(st['u_next'])
-            st['uG_cur'].copy_(st['uG_next'])
-            for p in range(I + 1, N + 1):  # parareal.py:408-416
-                if err[p, k] < eps:
-                    I += 1
-                else:
-                    break
-            st['I'] = I
+            I = self.device_advance(st, err[:, k])  # parareal.py:402-416
             if verbose == 'v' and rank == 0:
                 print('--> Converged:', I)
             conv_int.append(I)
