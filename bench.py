@@ -55,6 +55,12 @@ def parse():
     ap.add_argument("--replicated-sweep", action="store_true",
                     help="N>1: every rank runs the whole sweep (north_star's layout) instead of sharding the fits by dimension")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="fhn", choices=["fhn", "synthetic"],
+                    help="fhn: one nnGParareal iteration of BASELINE configs[3] (default, the headline); synthetic: BASELINE "
+                         "configs[4], the batched nnGP kernel sweep (kNN + N x d fits), queries split over the ranks")
+    ap.add_argument("--syn-n", type=int, default=16384, help="synthetic: dataset rows")
+    ap.add_argument("--syn-d", type=int, default=128, help="synthetic: dimension")
+    ap.add_argument("--syn-q", type=int, default=512, help="synthetic: queries (split over the ranks)")
     ap.add_argument("--iteration", type=int, default=0,
                     help="which nnGParareal iteration of the run a step is (0-based); the run is advanced there first")
     ap.add_argument("--later-iteration", type=int, default=3,
@@ -183,10 +189,156 @@ def workload_config(args):
             "l2": "256 MiB write between timed steps (L2 flush)"}
 
 
+def run_synthetic(args):
+    """BASELINE.json configs[4] / SURVEY.md section 8d config 5: X ~ U(-1,1)^{n x d}, Y = 1e-3 sin(X W), W ~ N(0,1)/sqrt(d),
+    Q queries = rows + 1e-3 N(0,1) (default_rng(0)), Nelder-Mead starts from default_rng(45).  The dataset is replicated,
+    the queries are split over the ranks (section 8e), the [Q, d] predictions are gathered at the end (one all-gather).
+    A step = kNN + the Q/W x d fits (9 searches + selection + posterior mean each) + the gather."""
+    import torch
+    import torch.distributed as dist
+    from nearest_neighbors_gparareal_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = _lib.default_handle(local)
+    n, d, m, Q = args.syn_n, args.syn_d, args.m, args.syn_q
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (n, d))
+    y = 1e-3 * np.sin(x @ (rng.standard_normal((d, d)) / np.sqrt(d)))
+    q_all = x[rng.permutation(n)[:Q]] + 1e-3 * rng.standard_normal((Q, d))
+    starts_all = np.random.default_rng(45).integers(-8, 0, (Q, d, 9, 1, 2)).astype(np.int8)
+    h.dataset_reset()
+    h.dataset_reserve(n, d)
+    h.dataset_append_host(x, y)
+    per = (Q + world - 1) // world
+    lo, hi = min(Q, rank * per), min(Q, (rank + 1) * per)
+    nq = hi - lo
+    q = torch.from_numpy(q_all[lo:hi].copy()).to(dev)
+    starts = torch.from_numpy(starts_all[lo:hi].copy()).to(dev)
+    idx = torch.empty((max(nq, 1), m), dtype=torch.int64, device=dev)
+    dst = torch.empty((max(nq, 1), m), dtype=torch.float64, device=dev)
+    pred_all = torch.zeros((world * per, d), dtype=torch.float64, device=dev)
+    pred = pred_all[rank * per:rank * per + max(nq, 1)]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        if nq > 0:
+            h.knn(q, nq, m, 0, idx, dst, stream)
+            h.fit_predict(q, idx, dst, nq, m, 1, starts, 0.1, 0.1, pred, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(pred_all, pred_all[rank * per:(rank + 1) * per])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+        flush.fill_(1)
+    h.counters(reset=True)
+    h.profile_read(reset=True)
+    h.profile_enable(True)
+    l0 = h.launch_count()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        step()
+        flush.fill_(1)
+    ev[1].record()
+    sync_all()
+    clk = clocks.stop()
+    t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    h.profile_enable(False)
+    prof = h.profile_read(reset=True)
+    nm_runs, nll_evals = h.counters(reset=True)
+    launches = (h.launch_count() - l0) // args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    knn_ms = prof["knn"][0] / args.steps
+    knn_bytes = 8.0 * n * d + 8.0 * nq * d + 16.0 * nq * m
+    fit_ms = prof["gp_fit"][0] / args.steps
+    fp64_peak = h.bench_fp64(20000)
+    fit_tf = (nll_evals / args.steps) * nll_flops(m) / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0
+    # e2e: host queries in, host predictions out (nngp_predict_host: H2D, kNN, fits, D2H), then the gather
+    e2e = None
+    if not args.no_e2e:
+        qh, sh = q_all[lo:hi].copy(), starts_all[lo:hi].copy()
+
+        def e2e_step():
+            ph = h.predict_host(qh, m, sh, 1, 0.1, 0.1)["pred"] if nq > 0 else np.zeros((0, d))
+            if world > 1:
+                buf = torch.zeros((world * per, d), dtype=torch.float64, device=dev)
+                buf[rank * per:rank * per + nq] = torch.from_numpy(ph).to(dev)
+                dist.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per])
+                return buf[:Q].cpu().numpy()
+            return ph
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = e2e_step()
+        sync_all()
+        secs = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs = float(tt.item())
+        e2e = {"value": Q * d / secs, "unit": "fits/s", "ms_per_step": 1e3 * secs, "steps": args.e2e_steps,
+               "h2d_bytes_per_step": int(nq * d * 8 + nq * d * 18), "d2h_bytes_per_step": int(nq * d * 8),
+               "finite": bool(np.all(np.isfinite(out))),
+               "api": "nngp_predict_host (NumPy queries + starts in, NumPy predictions out) + all-gather of [Q, d]"}
+    line = {"metric": METRIC, "value": Q * d / (ms_step * 1e-3), "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic nnGP kernel sweep (BASELINE configs[4]): kNN + batched N x d fits, queries split over ranks",
+                       "n_rows": n, "d": d, "m": m, "Q": Q, "n_restarts": 1, "jitters": 9,
+                       "l2": "256 MiB write between timed steps (L2 flush)"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "roofline": {"kernel": "sqdist_kernel<8> + select_kernel (kNN of this rank's queries)", "bound": "hbm" if nq < 16 else "fp64",
+                         "achieved": knn_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                         "frac": (knn_bytes / (knn_ms * 1e-3) / 1e9 / hbm) if knn_ms > 0 else None,
+                         "traffic": None, "knn_ms": knn_ms,
+                         "fp64_tflops": 3.0 * nq * n * d / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0,
+                         "note": "algorithmic bytes 8nd + 8Qd + 16Qm per call against MEASURED_PEAKS.json hbm_gbs; with Q >= 16 "
+                                 "queries per rank the exact (non-fused, 3 flops per coordinate) distance arithmetic is FP64-bound"},
+            "roofline_second_kernel": {"kernel": "gp_fit_grouped_kernel / gp_fit_predict_kernel", "bound": "fp64",
+                                       "achieved": fit_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                       "frac": fit_tf / fp64_peak if fp64_peak else None, "fit_ms": fit_ms},
+            "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] // args.steps} for k, v in prof.items()},
+            "fits_per_s": Q * d / (ms_step * 1e-3), "nm_runs_per_s_rank0": nm_runs / args.steps / (ms_step * 1e-3),
+            "nll_evals_per_s_rank0": nll_evals / args.steps / (ms_step * 1e-3),
+            "knn_gbs_rank0": knn_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else None}
+    if e2e:
+        line["e2e"] = e2e
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "synthetic":
+        run_synthetic(args)
         return
     import torch
     import torch.distributed as dist
