@@ -134,7 +134,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(args, n_dims_per_core, n_steps, warm):
+def cpu_sample(args, n_dims_per_core, n_steps, warm, dims_frac=1.0):
     """oracle (NumPy/SciPy port of the reference) on all host cores; returns the list of samples"""
     import warnings
     from oracle.cpu_baseline import FhnCpuSampler
@@ -143,7 +143,9 @@ def cpu_sample(args, n_dims_per_core, n_steps, warm):
     T = 1100.0 * args.slices / 512 if args.dx == 16 else 1100.0
     s = FhnCpuSampler(d_x=args.dx, N=args.slices, m=args.m, T=T, cores=cores)
     d = 2 * args.dx * args.dx
-    n_dims = min(d, max(cores, n_dims_per_core * cores))
+    # 8 sampled predicts, each over min(d, n_dims_per_core * cores) output dimensions: at d = 512 on 16
+    # cores that is 36 864 Nelder-Mead searches = ~2 minutes of CPU work, ~8 s of wall time
+    n_dims = 8 * max(min(d, cores), int(dims_frac * min(d, max(cores, n_dims_per_core * cores))))
     out = []
     for it in range(warm + n_steps):
         t0 = time.perf_counter()
@@ -160,7 +162,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    samples, cores, n_dims = cpu_sample(args, n_dims_per_core=1 << 20, n_steps=args.steps, warm=min(args.warmup, 1))
+    # a quarter of the output dimensions per sampled predict: K steps of ~2 s each keep the whole run within minutes
+    samples, cores, n_dims = cpu_sample(args, n_dims_per_core=1 << 20, n_steps=args.steps, warm=min(args.warmup, 1), dims_frac=0.25)
     t_iter = float(np.mean([r["t_iter"] for r in samples]))
     d = 2 * args.dx * args.dx
     sample = (f"per step: 8 predicts (queries spread over the slices) restricted to {max(1, n_dims // 8)} of {d} output dims each "
