@@ -369,21 +369,64 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       return bad;
     }
   }
-  // kernel entries of this lane, evaluated interleaved in groups of at most 8
+  // kernel entries of this lane.  Slot 0 first: the pairs are numbered e = i(i-1)/2 + j and lane l owns e = l + 32 t,
+  // so slot 0 of lanes 0..9 is the leading 5 x 5 block of the matrix.
   double v[NP];
-  {
-    constexpr int NV = NP;
+  v[0] = exp_neg(c * P.r2[0]);
+  if (!ALPHA) {
+    // Pivots 1..4 decided from the leading block alone, with exactly the operations the factorisation below
+    // performs on these entries (same fused multiply-adds in the same order: the decision is only anticipated).
+    // At a steady state 91 % of the failing evaluations fail here (first failing pivot 2: 40 %, 3: 37 %, 4: 13 %,
+    // profiles/r02/fit_failing_pivots.log) and they are 44 % of all evaluations: such an evaluation now costs
+    // one exponential and a 5 x 5 elimination instead of the whole kernel matrix, and the searches that run to
+    // SciPy's 400-evaluation limit on failing points -- the chain that ends a launch -- shrink by 3-4x.
+    const double k0 = P.pad[0] ? 0.0 : amp_s * v[0];
+    const double b10 = shfl(k0, 0), b20 = shfl(k0, 1), b30 = shfl(k0, 3), b40 = shfl(k0, 6);
+    double b21 = shfl(k0, 2), b31 = shfl(k0, 4), b32 = shfl(k0, 5), b41 = shfl(k0, 7), b42 = shfl(k0, 8),
+           b43 = shfl(k0, 9);
+    const double ip0 = rcp_pos(dd0);
+    double w1 = b10 * ip0, w2 = b20 * ip0, w3 = b30 * ip0, w4 = b40 * ip0;
+    const double d1 = fma(-w1, b10, dd0);
+    double d2 = fma(-w2, b20, dd0), d3 = fma(-w3, b30, dd0), d4 = fma(-w4, b40, dd0);
+    b21 = fma(-w2, b10, b21); b31 = fma(-w3, b10, b31); b41 = fma(-w4, b10, b41);
+    b32 = fma(-w3, b20, b32); b42 = fma(-w4, b20, b42);
+    b43 = fma(-w4, b30, b43);
+    const double ip1 = rcp_pos(d1);
+    w2 = b21 * ip1; w3 = b31 * ip1; w4 = b41 * ip1;
+    d2 = fma(-w2, b21, d2); d3 = fma(-w3, b31, d3); d4 = fma(-w4, b41, d4);
+    b32 = fma(-w3, b21, b32); b42 = fma(-w4, b21, b42);
+    b43 = fma(-w4, b31, b43);
+    const double ip2 = rcp_pos(d2);
+    w3 = b32 * ip2; w4 = b42 * ip2;
+    d3 = fma(-w3, b32, d3); d4 = fma(-w4, b42, d4);
+    b43 = fma(-w4, b32, b43);
+    const double ip3 = rcp_pos(d3);
+    w4 = b43 * ip3;
+    d4 = fma(-w4, b43, d4);
+    // a failed pivot makes the later ones meaningless, exactly as in the loop below (ok stays false)
+    const bool fail = !(d1 > pmin) || !(d2 > pmin) || !(d3 > pmin) || !(d4 > pmin);
+    if (__any_sync(FULL, fail)) {
+      GpOut bad;
+      bad.amp = amp;
+      bad.c = c;
+      bad.ok = false;
+      bad.val = dinf();
+      return bad;
+    }
+  }
+  if constexpr (NP > 1) {
+    constexpr int NV = NP - 1;
     constexpr int G = (NV <= 8) ? NV : (NV + 1) / 2;
     double xin[NV];
 #pragma unroll
-    for (int t = 0; t < NP; t++) xin[t] = c * P.r2[t];
+    for (int t = 0; t < NV; t++) xin[t] = c * P.r2[t + 1];
     {
       double xa[G], oa[G];
 #pragma unroll
       for (int t = 0; t < G; t++) xa[t] = xin[t];
       exp_neg_vec<G>(xa, oa);
 #pragma unroll
-      for (int t = 0; t < G; t++) v[t] = oa[t];
+      for (int t = 0; t < G; t++) v[t + 1] = oa[t];
     }
     if constexpr (NV > G) {
       constexpr int G2 = NV - G;
@@ -392,7 +435,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       for (int t = 0; t < G2; t++) xa[t] = xin[G + t];
       exp_neg_vec<G2>(xa, oa);
 #pragma unroll
-      for (int t = 0; t < G2; t++) v[G + t] = oa[t];
+      for (int t = 0; t < G2; t++) v[G + t + 1] = oa[t];
     }
   }
 #pragma unroll
@@ -452,7 +495,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     // (at the FHN target 14 % of the searches, 57 % of the evaluations, and the serial chain that ends
     // the launch).  Near-duplicate neighbours fail at the first pivots: leave early at a few fixed
     // steps (warp-uniform vote, so the shuffles below stay convergent).
-    if (!ALPHA && (k == 1 || k == 2 || k == 4 || k == 8 || k == 14) && k < M - 1) {
+    if (!ALPHA && (k == 6 || k == 8 || k == 11 || k == 14) && k < M - 1) {
       if (__any_sync(FULL, !ok)) {
         GpOut bad;
         bad.amp = amp;
