@@ -179,7 +179,14 @@ class Parareal():
             kw = dict(kwargs)
             pool = kw.pop('pool')
             return CudaNNGP(n=self.n, N=self.N, worker_pool=pool, **kw)
-        # 'gpjax' (full GParareal) and 'elm' are outside the nnGParareal hot path
+        if name == 'gpjax':
+            if 'pool' not in kwargs:
+                raise Exception('A worker pool must be provided to run NNGP in parallel')
+            from .gp_full import CudaGP
+            kw = dict(kwargs)
+            pool = kw.pop('pool')
+            return CudaGP(n=self.n, N=self.N, worker_pool=pool, **kw)
+        # 'elm' is outside the scope (not in the paper's results or configurations)
         raise Exception('Not implemented')
 
     def _run(self, model='parareal', cstm_mdl_name=None, add_model=False, **kwargs):

@@ -128,6 +128,48 @@ def run_case(name):
     print(name, "K", K, "conv_int", out["conv_int"], f"{secs:.1f}s", "samples", len(samples), flush=True)
 
 
+GP_CASES = {
+    # GParareal (models.py:273-473, `GPjax_p`): the full-dataset GP, needed for the three-way comparison of BASELINE configs[2]
+    "burgers_d32_N32_gp": ("burgers", dict(N=32, d_x=32), {}, 5e-7),
+    "lorenz_N32_gp": ("lorenz", dict(N=32), {}, 5e-7),
+}
+
+
+def run_gp_case(name):
+    """runs the unmodified reference with model='gpjax' and records K, conv_int, err, the final iterate, the dataset
+    and the hyper-parameters / jitters selected in every iteration (GPjax_p.hyp, models.py:281, 425-426)"""
+    ns = load_reference(fast_kernel=True)
+    system, bkw, mkw, eps = GP_CASES[name]
+    ode, cfg = _build(ns, system, **bkw)
+    solver = ns.solver.SolverRK(ode.get_vector_field(), use_jax=False, **cfg)
+    trace = []
+
+    class Recording(ns.models.GPjax_p):
+        def fit(self, x, y, k, *a, **kw):
+            super().fit(x, y, k, *a, **kw)
+            trace.append((k, x.shape[0], np.array(self.thetas, dtype=float).copy(), np.array(self.jitters, dtype=float).copy()))
+
+    class P(ns.parareal.Parareal):
+        def _run(self, **kwargs):
+            mdl = Recording(n=self.n, N=self.N, worker_pool=kwargs["pool"], **mkw)
+            return self._parareal(mdl, **kwargs)
+
+    p = P(ode, solver, epsilon=eps, verbose="", **cfg)
+    t0 = time.time()
+    workers = int(os.environ.get("NNGP_GOLDEN_POOL", "0"))
+    out = p.run(pool=workers) if workers > 0 else p.run()
+    secs = time.time() - t0
+    K = out["k"]
+    arrays = dict(K=K, conv_int=np.array(out["conv_int"]), err=out["err"], u_last=out["u"][:, :, -1], x=out["x"], D=out["D"],
+                  t=out["t"], u0=ode.get_init_cond(), seconds=secs,
+                  cfg=json.dumps({k: (v if not isinstance(v, np.ndarray) else v.tolist()) for k, v in cfg.items()}),
+                  model_kwargs=json.dumps(mkw), epsilon=eps, n_fits=len(trace))
+    for i, (k, rows, th, jit) in enumerate(trace):
+        arrays[f"f{i}_k"], arrays[f"f{i}_rows"], arrays[f"f{i}_thetas"], arrays[f"f{i}_jitters"] = k, rows, th, jit
+    np.savez_compressed(os.path.join(OUT, f"run_{name}.npz"), **arrays)
+    print(name, "K", K, "conv_int", out["conv_int"], f"{secs:.1f}s", flush=True)
+
+
 def rk_vectors():
     """Known answers of RK.py (`_RK_numpy_` via run_get_last) and systems.py vector fields."""
     ns = load_reference()
@@ -266,5 +308,7 @@ if __name__ == "__main__":
             rk_full_vectors()
         elif item == "published":
             published()
+        elif item in GP_CASES:
+            run_gp_case(item)
         else:
             run_case(item)

@@ -27,12 +27,15 @@ torch.cuda.synchronize()
 print("ok", h.counters())
 if os.environ.get("NFEV_HIST"):
     import numpy as np
-    q = st["u_next"][1].cpu().numpy()
+    q = st["u_next"][st["I"] + n_slices - 1].cpu().numpy()
     out = h.predict_host(q[None], m, model.draw_starts(1), 1, 0.1, 0.1, details=True)
     nf = out["nfev"].ravel()
     print("nfev: mean", nf.mean(), "median", np.median(nf), "p90", np.percentile(nf, 90), "p99", np.percentile(nf, 99),
           "max", nf.max(), "count>=200", int((nf >= 200).sum()), "count==400", int((nf >= 400).sum()))
     fv = out["fvals"].ravel()
+    print("nfev==400 with finite fval", int(((nf >= 400) & np.isfinite(fv)).sum()), "nfev>=150 finite", int(((nf >= 150) & np.isfinite(fv)).sum()),
+          "nfev>=100 finite", int(((nf >= 100) & np.isfinite(fv)).sum()), "max nfev among finite", int(nf[np.isfinite(fv)].max()))
+    print("nfev histogram (finite searches):", np.histogram(nf[np.isfinite(fv)], bins=[0, 30, 50, 70, 100, 150, 200, 300, 401])[0])
     print("inf fvals", int(np.isinf(fv).sum()), "of", fv.size)
     long = np.argsort(nf)[-8:]
     for t in long:

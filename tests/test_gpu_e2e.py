@@ -237,3 +237,34 @@ def test_published_K_distribution_without_bias():
     assert v.size >= 90
     assert abs(v.mean()) <= 0.25, v.mean()
     assert np.mean(v == 0) >= 0.45 and np.mean(np.abs(v) <= 1) >= 0.90
+
+
+@pytest.mark.parametrize("name", ["lorenz_N32_gp", "burgers_d32_N32_gp"])
+def test_gparareal_full_gp_model_against_reference_run(name):
+    """model='gpjax' (GParareal, models.py:273-473: one GP on the whole dataset per output dimension, warm-started
+    Nelder-Mead over 9 jitters) through the host driver, against a run of the unmodified reference: same K (+-1 where
+    the run is borderline), the same converged-slice counts while the dataset is small, final iterate inside the
+    Parareal tolerance of the fine solution."""
+    import os
+    from helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, f"run_{name}.npz")):
+        pytest.skip("fixture not generated")
+    z, cfg, mkw = load_run(name)
+    key, kw = case_system(name)
+    ode = device_system(key, **kw)
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **{k: cfg[k] for k in ("Ng", "Nf", "F", "G")})
+    p = nn.Parareal(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=float(z["epsilon"]), verbose='')
+    out = p.run(model='gpjax', pool=nn.CudaPool(), parall='mpi')
+    ref_conv = [int(v) for v in z["conv_int"]]
+    print(f"{name}: GParareal on the device K={out['k']} conv_int={out['conv_int']} (reference K={int(z['K'])} {ref_conv})")
+    assert out['converged'] and abs(out['k'] - int(z["K"])) <= 1
+    assert out['conv_int'][:3] == ref_conv[:3]
+    N = cfg["N"]
+    fine = np.zeros_like(out['u_last'])
+    fine[0] = p.u0
+    for i in range(N):
+        fine[i + 1] = p.solver.run_F(out['t'][i], out['t'][i + 1], fine[i])
+    acc, acc_ref = np.max(np.abs(out['u_last'] - fine)), np.max(np.abs(z["u_last"] - fine))
+    assert acc <= max(float(z["epsilon"]), 3 * acc_ref), (acc, acc_ref)
+    for key_ in ('serial_train_time', 'avg_serial_train_time', 'mdl_train_t', 'mdl_pred_t'):
+        assert key_ in out['timings']

@@ -325,3 +325,36 @@ def test_reference_side_binding_derives_from_reference_classes():
     assert np.array_equal(ode.get_init_cond(), nn.FHN_PDE(d_x=4).get_init_cond())
     with pytest.raises(Exception, match="instance of the ODE class"):
         ref.parareal.Parareal(object(), solver, **cfg)
+
+
+def test_lockstep_nelder_mead_equals_scipy_bit_for_bit():
+    """gp_full._NM (the step-function Nelder-Mead that drives the batched GParareal fits) against the installed
+    scipy.optimize.minimize on objectives with flat valleys, +inf regions and evaluation-limit runs"""
+    from scipy.optimize import minimize
+    from nearest_neighbors_gparareal_b200.gp_full import _NM
+    rng = np.random.default_rng(3)
+
+    def rosen(x):
+        return (1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+
+    def walled(x):
+        return np.inf if x[0] < 0.3 else (x[0] - 1) ** 2 + abs(x[1]) ** 1.5
+
+    def all_inf(x):
+        return np.inf
+
+    def noisy(x):
+        return np.sin(5 * x[0]) * np.cos(3 * x[1]) + 0.1 * x[0] ** 2 + 0.1 * x[1] ** 2
+
+    for f in (rosen, walled, all_inf, noisy):
+        for _ in range(6):
+            x0 = rng.uniform(-2, 2, 2) if f is not walled else np.array([rng.uniform(0.31, 2), rng.uniform(-1, 1)])
+            for tol in (1e-4, 1e-1):
+                nm = _NM(x0, tol, tol)
+                while not nm.done:
+                    nm.step(float(f(nm.pt)))
+                x, fv = nm.result()
+                with np.errstate(all="ignore"):
+                    ref = minimize(f, x0, method='Nelder-Mead', options={'fatol': tol, 'xatol': tol})
+                assert nm.fcalls == ref.nfev, (f.__name__, x0, nm.fcalls, ref.nfev)
+                assert np.array_equal(x, ref.x) and (fv == ref.fun or (np.isinf(fv) and np.isinf(ref.fun)))
