@@ -31,7 +31,8 @@ extern "C" {
 typedef struct nngp_handle_s* nngp_handle_t;
 
 #define NNGP_ABI_VERSION 1
-#define NNGP_MAX_NEIGHBOURS 32 /* m <= 32: one lane per neighbour row */
+#define NNGP_MAX_NEIGHBOURS 32 /* m <= 32: one lane per neighbour row (the fast kernels) */
+#define NNGP_MAX_NEIGHBOURS_BIG 160 /* 32 < m <= 160 (nn='adaptive' past iteration 30): one CTA per search, matrix in shared memory */
 #define NNGP_N_JITTER 9        /* models.py:186  jitter = arange(-20,-11) */
 
 /* system ids: the vector fields of systems.py */

@@ -784,6 +784,7 @@ __device__ __noinline__ double posterior_mean(double th0, double th1, double jit
 }
 
 #include "gpfit_group.cuh"
+#include "gpfit_big.cuh"
 
 // registers per thread: 4-warp CTAs, K CTAs per SM
 #ifndef FIT_OCC20
@@ -1048,6 +1049,13 @@ int gp_prep_launch(nngp_handle_t h, const long long* d_idx, int nq, int m, doubl
                    cudaStream_t st) {
   if (nq <= 0) return 0;
   ProfScope prof(h, 2, st);
+  if (m > NNGP_MAX_NEIGHBOURS) {
+    const long long total = (long long)nq * (m * (m + 1) / 2);
+    gp_prep_big_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_idx, h->ds_x, h->ds_d, m, nq, d_r2);
+    h->launches++;
+    NNGP_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   gp_prep_kernel<<<nq, 256, 0, st>>>(d_idx, h->ds_x, h->ds_d, m, d_r2);
   h->launches++;
   NNGP_CUDA(h, cudaGetLastError());
@@ -1103,6 +1111,28 @@ static int fit_grouped_launch_m(nngp_handle_t h, const FitArgs& A, int nqj, cuda
   return 0;
 }
 
+// 32 < m <= NNGP_MAX_NEIGHBOURS_BIG: one CTA per search, matrix in shared memory (gpfit_big.cuh)
+static int fit_big_launch(nngp_handle_t h, const FitArgs& A, int nqj, cudaStream_t st) {
+  const int m = A.m, ld = m | 1;
+  const size_t smem = sizeof(double) * ((size_t)m * ld + 3 * (size_t)m + 8);
+  if (!h->attr_big) {
+    const int maxs = (int)(sizeof(double) * ((size_t)NNGP_MAX_NEIGHBOURS_BIG * (NNGP_MAX_NEIGHBOURS_BIG | 1) + 3 * NNGP_MAX_NEIGHBOURS_BIG + 8));
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    NNGP_CUDA(h, cudaFuncSetAttribute(gp_select_mean_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    h->attr_big = true;
+  }
+  int occ = 1;
+  NNGP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gp_fit_big_kernel, BIG_THREADS, smem));
+  long long blocks = (long long)h->sm_count * (occ < 1 ? 1 : occ);
+  if (blocks > A.ntasks) blocks = A.ntasks;
+  ProfScope prof(h, 3, st);
+  gp_fit_big_kernel<<<(unsigned)blocks, BIG_THREADS, smem, st>>>(A);
+  gp_select_mean_big_kernel<<<nqj, BIG_THREADS, smem, st>>>(A, nqj);
+  h->launches += 2;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 #define DISPATCH_CASE(MMV, CALL) else if ((m) <= MMV) { constexpr int MM = MMV; CALL; }
 #define DISPATCH_M(m, CALL)                                                   \
   do {                                                                        \
@@ -1123,7 +1153,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
                           double* d_fval_opt, int* d_nfev, double* d_fvals, double* d_thetas,
                           cudaStream_t st, int j0, int dl) {
   if (nq <= 0) return 0;
-  if (m < 1 || m > NNGP_MAX_NEIGHBOURS) return nngp_fail(h, "fit: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS);
+  if (m < 1 || m > NNGP_MAX_NEIGHBOURS_BIG) return nngp_fail(h, "fit: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS_BIG);
   if (R < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", R);
   const int d = h->ds_d;
   if (dl < 0) dl = d;
@@ -1142,6 +1172,7 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
   A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
+  if (m > NNGP_MAX_NEIGHBOURS) return fit_big_launch(h, A, nq * dl, st);
   int rc = 0;
   const bool grouped = (h->fit_mode == 2) || (h->fit_mode == 0 && nq >= 4 && m <= 20);
   if (!grouped) {

@@ -493,6 +493,48 @@ sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ 
 }
 
 
+// m > 32 (rare: nn='adaptive' past iteration 30): m passes of "smallest key above the last one" by one CTA per query
+__global__ void __launch_bounds__(256)
+select_big_kernel(const double* __restrict__ dist, long long n, int m, long long* __restrict__ idx_out,
+                  double* __restrict__ dist_out) {
+  __shared__ double sd[256];
+  __shared__ long long si[256];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const double* dq = dist + (long long)q * n;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const long long IMAX = 0x7fffffffffffffffLL;
+  double ld = 0.0;
+  long long li = -1;
+  for (int t = 0; t < m; t++) {
+    double bd = INF;
+    long long bi = IMAX;
+    for (long long i = tid; i < n; i += 256) {
+      const double v = dq[i];
+      if ((t == 0 || key_less(ld, li, v, i)) && key_less_pad(v, i, bd, bi)) {
+        bd = v;
+        bi = i;
+      }
+    }
+    sd[tid] = bd;
+    si[tid] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o && key_less_pad(sd[tid + o], si[tid + o], sd[tid], si[tid])) {
+        sd[tid] = sd[tid + o];
+        si[tid] = si[tid + o];
+      }
+      __syncthreads();
+    }
+    ld = sd[0];
+    li = si[0];
+    if (tid == 0) {
+      idx_out[(long long)q * m + t] = li;
+      dist_out[(long long)q * m + t] = ld;
+    }
+    __syncthreads();
+  }
+}
+
 static constexpr long long KNN_CHUNK = 4096;  // rows up to which one CTA selects alone; chunks are >= a quarter of it
 
 // Rows per first-level CTA: the scan of one query is split only as far as it takes to fill the GPU
@@ -521,8 +563,8 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
                long long* d_idx, double* d_dist, void* ws, cudaStream_t st) {
   const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
   if (nq <= 0) return 0;
-  if (m < 1 || m > NNGP_MAX_NEIGHBOURS)
-    return nngp_fail(h, "knn: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS);
+  if (m < 1 || m > NNGP_MAX_NEIGHBOURS_BIG)
+    return nngp_fail(h, "knn: m=%d outside [1,%d]", m, NNGP_MAX_NEIGHBOURS_BIG);
   if (n > h->ds_rows) return nngp_fail(h, "knn: n_rows=%lld > dataset rows %lld", n, h->ds_rows);
   if (n < m) return nngp_fail(h, "knn: dataset has %lld rows, fewer than m=%d", n, m);
   const int d = h->ds_d;
@@ -546,7 +588,10 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
   NNGP_CUDA(h, cudaGetLastError());
   const long long chunk_rows = knn_chunk_rows(nq, n);
   const long long chunks = (n + chunk_rows - 1) / chunk_rows;
-  if (chunks == 1) {
+  if (m > NNGP_MAX_NEIGHBOURS) {
+    select_big_kernel<<<nq, 256, 0, st>>>(dist, n, m, d_idx, d_dist);
+    h->launches++;
+  } else if (chunks == 1) {
     select_kernel<<<dim3(1, nq), KNN_SEL_THREADS, 0, st>>>(dist, nullptr, n, n, m, d_idx, d_dist);
     h->launches++;
   } else {
@@ -565,7 +610,7 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
 
 // scan + selection + neighbour matrix of ONE query in one launch; false when the shape needs the general path
 bool knn_prep_fused_ok(nngp_handle_t h, long long n, int m) {
-  return n <= KNN_CHUNK && n >= m && (size_t)h->ds_d * sizeof(double) <= 48 * 1024;
+  return m <= NNGP_MAX_NEIGHBOURS && n <= KNN_CHUNK && n >= m && (size_t)h->ds_d * sizeof(double) <= 48 * 1024;
 }
 
 int knn_prep_fused_launch(nngp_handle_t h, const double* d_q, int m, long long n, long long* d_idx, double* d_dist,

@@ -155,8 +155,8 @@ class CudaNNGP(ModelAbstr):
         details = kwargs.get('return_details', False)
         h = self.handle()
         m = min(self.neighbours(), self._n_dev)
-        if m > 32:
-            raise Exception('nn > 32 neighbours is not supported by the warp-per-matrix GP kernel')
+        if m > 160:
+            raise Exception('nn > 160 neighbours is not supported (include/nngpara.h: NNGP_MAX_NEIGHBOURS_BIG)')
         new_x = np.asarray(new_x, dtype=float).reshape(1, -1)
         starts = self.draw_starts(1)
         s = time.time()

@@ -439,8 +439,8 @@ class PararealDevice(Parareal):
             model.k = k
             model.time_k = k
             m = min(model.neighbours(k), h.dataset_rows())
-            if m > 32:
-                raise Exception('nn > 32 neighbours is not supported by the warp-per-matrix GP kernel')
+            if m > 160:
+                raise Exception('nn > 160 neighbours is not supported (include/nngpara.h: NNGP_MAX_NEIGHBOURS_BIG)')
             if starts is None:
                 starts = torch.from_numpy(model.draw_starts(N - I)).to(st['dev'])
             st['starts'] = starts  # keep alive until the stream has consumed it

@@ -268,3 +268,16 @@ def test_gparareal_full_gp_model_against_reference_run(name):
     assert acc <= max(float(z["epsilon"]), 3 * acc_ref), (acc, acc_ref)
     for key_ in ('serial_train_time', 'avg_serial_train_time', 'mdl_train_t', 'mdl_pred_t'):
         assert key_ in out['timings']
+
+
+def test_adaptive_neighbour_count_beyond_32_iterations():
+    """nn='adaptive' with a run that needs more than 30 iterations (m = k + 2 > 32): plain-Parareal-hard Lorenz with a
+    crude coarse solver; the device driver must keep going through the large-m path and converge"""
+    ode = nn.Lorenz(normalization='-11')
+    cfg = nn.Config(ode).get()
+    cfg.update(Ng=2, G='RK1', N=48, tspan=[0, 18 * 48 / 50])
+    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+    out = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=5e-9, verbose='').run(
+        model='nngp', nn='adaptive', seed=45)
+    print("adaptive run: K", out['k'], out['conv_int'])
+    assert out['converged'] and np.all(np.isfinite(out['u']))

@@ -550,7 +550,7 @@ def test_empty_and_extreme_inputs(handle):
     with pytest.raises(_lib.NNGPError, match="fewer than m"):
         handle.knn_host(q, 32, n_rows=20)
     with pytest.raises(_lib.NNGPError, match="outside"):
-        handle.predict_host(q, 33, rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8), 1, 0.1, 0.1)
+        handle.predict_host(q, 161, rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8), 1, 0.1, 0.1)
 
 
 def test_predict_dimension_blocks_equal_full_predict(handle):
@@ -798,3 +798,43 @@ def test_grouped_search_kernel_equals_one_search_per_warp_bitwise(handle, n, d, 
     for key in ("idx", "nfev", "thetas", "fvals", "theta_opt", "fval_opt", "jitter_opt", "pred"):
         assert np.array_equal(res["warp"][key], res["grouped"][key], equal_nan=True), key
     assert np.isinf(res["warp"]["fvals"]).sum() > 0 and np.isfinite(res["warp"]["fvals"]).sum() > 0
+
+
+@pytest.mark.parametrize("n,d,m", [(300, 3, 33), (400, 3, 48), (500, 2, 64), (700, 3, 100), (400, 4, 160)])
+def test_more_than_32_neighbours(handle, n, d, m):
+    """nn='adaptive' gives m = max(10, k+2) (models.py:172-175): past iteration 30 the neighbour set exceeds one lane
+    per row.  The large-m path (one CTA per search, matrix in shared memory) against the oracle: neighbour indices
+    bit-exact, searches mostly on SciPy's trajectory, objective and posterior mean at the device's optimum equal to
+    the oracle's (LAPACK) where the matrix is well conditioned."""
+    rng = np.random.default_rng(60 + m)
+    x, y = make_dataset(rng, n, d)
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    q = x[7:8] + 1e-3 * rng.standard_normal((1, d))
+    starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+    out = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+    oi, okq = onn.knn(q[0], x, m)
+    assert np.array_equal(out["idx"][0], oi)
+    r2 = onn.pairwise_sqdist(x[oi], x[oi])
+    same = total = checked = 0
+    for j in range(d):
+        for a in range(9):
+            th, fv, ne = onn.nm_run(r2, y[oi, j], starts[0, j, a, 0].astype(float), onn.JITTERS[a], 0.1, 0.1)
+            total += 1
+            same += bool(np.array_equal(out["thetas"][0, j, a, 0], th) and out["nfev"][0, j, a, 0] == ne)
+        best = onn.select(out["fvals"][0, j, :, 0])
+        assert out["jitter_opt"][0, j] == -20 + best and out["fval_opt"][0, j] == out["fvals"][0, j, best, 0]
+        th_o, jit_o = out["theta_opt"][0, j], out["jitter_opt"][0, j]
+        K = onn.se_kernel_from_r2(r2, th_o) + np.eye(m) * 10 ** jit_o
+        cond = np.linalg.cond(K)
+        want_f = onn.neg_log_lik(r2, y[oi, j], th_o, jit_o)
+        want_p = onn.posterior_mean(r2, okq, y[oi, j], th_o, jit_o)
+        assert np.isfinite(out["pred"][0, j])
+        if cond < 1e8 and np.isfinite(want_f):
+            checked += 1
+            assert abs(out["fval_opt"][0, j] - want_f) <= 1e-8 * max(1.0, abs(want_f)), (j, cond)
+            assert abs(out["pred"][0, j] - want_p) <= max(1e-8, 4 * cond * 2.2e-16) * abs(want_p) + 1e-14, (j, cond)
+    assert np.all(out["nfev"] >= 3) and np.all(out["nfev"] <= 400)
+    print(f"m={m}: {same}/{total} searches on the oracle's trajectory, {checked}/{d} optima well conditioned")
+    assert same >= 0.4 * total
