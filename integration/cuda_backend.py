@@ -99,5 +99,18 @@ def bind(ref_dir=None):
 
     CudaPool = pkg.CudaPool
     B.CudaSolverRK, B.CudaNNGP, B.CudaParareal = CudaSolverRK, CudaNNGP, CudaParareal
+    # module-level names: the reference pickles the driver and the model copy (parareal.py:114-139, models.py:64-72),
+    # and pickle stores classes by module + qualified name
+    for cls in [CudaSolverRK, CudaNNGP, CudaParareal] + [getattr(B, n) for n in _SYSTEMS]:
+        cls.__module__, cls.__qualname__ = __name__, cls.__name__
+        globals()[cls.__name__] = cls
     _bound = B
     return B
+
+
+def __getattr__(name):
+    """unpickling a dump written through this binding looks the classes up here: bind on first use"""
+    if name in ("CudaSolverRK", "CudaNNGP", "CudaParareal") + _SYSTEMS:
+        bind()
+        return globals()[name]
+    raise AttributeError(name)

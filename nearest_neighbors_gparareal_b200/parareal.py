@@ -22,6 +22,7 @@ from .pool import CudaPool, MyPool
 from .solver import CudaSolverRK, SolverAbstr
 from .systems import ODE
 from .utils import dim_block
+from .checkpoint import RunHistory, adopt_model, state_from_objs
 
 
 def slice_block(I, N, rank, world):
@@ -149,9 +150,9 @@ class Parareal():
         self.f = self.ode.get_vector_field()
         self.u0 = self.ode.get_init_cond()
         objs = other.objs
-        run_kwargs = dict(objs['kwargs'])
+        run_kwargs = {k: v for k, v in dict(objs['kwargs']).items() if k not in ('_reload_objs', '_run_from_int')}
         run_kwargs.update(kwargs)
-        mdl = other.mdl
+        mdl = adopt_model(other.mdl, self.n, self.N)  # also dumps written by the reference (checkpoint.py)
         base_time = objs['F_time'] + objs['G_time'] + mdl.get_times()['mdl_tot_t']
         return self.run(mdl, base_time, cstm_mdl_name, add_model, _run_from_int=True, _reload_objs=objs, **run_kwargs)
 
@@ -225,13 +226,14 @@ class Parareal():
         k0 = 0
         if _load_mdl:
             # resume (parareal.py:279-297): state after iteration k of the stored run
-            o = _reload_objs
-            I, conv_int, err = o['I'], list(o['conv_int']), o['err'].copy()
-            cur = {key: o[key].copy() for key in ('u', 'uG', 'uF')}
+            o = state_from_objs(_reload_objs)
+            I, conv_int, err = o['I'], o['conv_int'], o['err']
+            cur = {key: o[key] for key in ('u', 'uG', 'uF')}
             nxt = {key: a.copy() for key, a in cur.items()}
-            history = [h.copy() for h in o['history']]
-            x, D = o['x'].copy(), o['D'].copy()
-            G_time, F_time, F_time_serial = o['G_time'], o['F_time'], o.get('F_time_serial', 0)
+            rec = RunHistory.from_objs(_reload_objs)
+            history = [h.copy() for h in rec.u]
+            x, D = o['x'], o['D']
+            G_time, F_time, F_time_serial = o['G_time'], o['F_time'], _reload_objs.get('F_time_serial', 0)
             k0 = o['k'] + 1
         else:
             # coarse initialisation (parareal.py:264-277)
@@ -245,6 +247,7 @@ class Parareal():
             history = [cur['u'].copy()]
             x = np.zeros((0, n))
             D = np.zeros((0, n))
+            rec = RunHistory(N, n, cur['u'], cur['uG']) if store_int else None
         k = max(k0 - 1, 0)
         for k in range(k0, N):
             if verbose == 'v':
@@ -269,6 +272,8 @@ class Parareal():
             # training data (parareal.py:336-339)
             x = np.vstack([x, cur['u'][I - 1:N]])
             D = np.vstack([D, cur['uF'][I:N + 1] - cur['uG'][I:N + 1]])
+            if store_int and rec is not None:
+                rec.add_fine(cur['uF'], I, cur['u'][I - 1:N], cur['uF'][I:N + 1] - cur['uG'][I:N + 1])
             if I == N:
                 if verbose == 'v':
                     print('WARNING: early stopping')
@@ -302,16 +307,16 @@ class Parareal():
                 print('--> Converged:', I)
             conv_int.append(I)
             if store_int:
-                # parareal.py:420-431; the state is kept PararealLight-style (current iterate + history of u),
-                # so the dump holds u / uG / uF of iteration k+1 rather than the (N+1, d, k+2) arrays
+                # parareal.py:420-431, the reference's key set and array layout (checkpoint.py)
+                rec.add_iterate(cur['u'], cur['uG'])
                 name_base = kwargs.get('int_name', f'{self.ode_name}_{self.N}_{model.name}_int')
                 int_dir = kwargs.get('int_dir', '')
-                _objs = {'t': t, 'I': I, 'verbose': verbose, 'u': cur['u'], 'uG': cur['uG'], 'uF': cur['uF'],
-                         'history': history, 'err': err, 'x': x, 'D': D, 'G_time': G_time, 'F_time': F_time,
+                u3, uG3, uF3, data_x, data_D = rec.arrays(k, I)
+                run_kw = {kk: vv for kk, vv in kwargs.items() if kk not in ('_reload_objs',)}
+                _objs = {'t': t, 'I': I, 'verbose': verbose, 'u': u3, 'uG': uG3, 'uF': uF3, 'err': err[:, :k + 2],
+                         'x': x, 'D': D, 'data_x': data_x, 'data_D': data_D, 'G_time': G_time, 'F_time': F_time,
                          'F_time_serial': F_time_serial, 'debug': debug, 'early_stop': early_stop, 'parall': parall,
-                         'store_int': store_int, 'kwargs': dict(kwargs, debug=debug, early_stop=early_stop,
-                                                                parall=parall, store_int=store_int),
-                         'k': k, 'conv_int': conv_int}
+                         'store_int': store_int, 'kwargs': run_kw, 'k': k, 'conv_int': conv_int}
                 self.store(path=os.path.join(int_dir, name_base), name=f'{name_base}_{k}', mdl=model, objs=_objs)
             if I == N:
                 break
@@ -487,8 +492,6 @@ class PararealDevice(Parareal):
     def _parareal(self, model, early_stop=None, parall='Serial', store_int=False, max_rows=None,
                   iteration_hook=None, **kwargs):
         import torch
-        if store_int:
-            raise NotImplementedError('intermediate checkpoints are outside the hot path')
         N, eps = self.N, self.epsilon
         verbose = kwargs.get('verbose', self.verbose)
         tic = time.time()
@@ -499,6 +502,12 @@ class PararealDevice(Parareal):
         rank = st['rank']
         conv_int = []
         err = np.full((N + 1, N), np.nan)
+        # store_int: the reference's per-iteration dumps (parareal.py:420-431) -- the device state of every iteration is
+        # copied to the host (3 x (N+1) x n doubles) and written in the reference's layout (checkpoint.py); rank 0 only
+        rec = xs = Ds = None
+        if store_int:
+            rec = RunHistory(N, self.n, st['u_cur'].cpu().numpy(), st['uG_cur'].cpu().numpy())
+            xs, Ds = [], []
         k = 0
         for k in range(N):
             if verbose == 'v' and rank == 0:
@@ -507,6 +516,12 @@ class PararealDevice(Parareal):
             self.device_fine_step(st)
             torch.cuda.synchronize(st['dev'])
             F_time += time.time() - tic
+            if store_int:
+                I1 = st['I']
+                uc, uf, ug = st['u_cur'].cpu().numpy(), st['uF'][:N + 1].cpu().numpy(), st['uG_cur'].cpu().numpy()
+                xs.append(uc[I1 - 1:N])
+                Ds.append(uf[I1:N + 1] - ug[I1:N + 1])
+                rec.add_fine(uf, I1, xs[-1], Ds[-1])
             tic = time.time()
             self.device_sweep(st, k)
             I = st['I']
@@ -532,6 +547,21 @@ class PararealDevice(Parareal):
             if verbose == 'v' and rank == 0:
                 print('--> Converged:', I)
             conv_int.append(I)
+            if store_int:
+                rec.add_iterate(st['u_cur'].cpu().numpy(), st['uG_cur'].cpu().numpy())
+                if rank == 0:
+                    name_base = kwargs.get('int_name', f'{self.ode_name}_{self.N}_{model.name}_int')
+                    u3, uG3, uF3, data_x, data_D = rec.arrays(k, I)
+                    x_all, D_all = np.vstack(xs), np.vstack(Ds)
+                    if st['is_gp']:
+                        model.x, model.y = x_all, D_all   # the resumed run re-uploads the dataset from the model copy
+                    run_kw = {kk: vv for kk, vv in kwargs.items() if kk not in ('_reload_objs',)}
+                    _objs = {'t': st['t_host'], 'I': I, 'verbose': verbose, 'u': u3, 'uG': uG3, 'uF': uF3, 'err': err[:, :k + 2],
+                             'x': x_all, 'D': D_all, 'data_x': data_x, 'data_D': data_D, 'G_time': G_time, 'F_time': F_time,
+                             'debug': False, 'early_stop': early_stop, 'parall': parall, 'store_int': store_int,
+                             'kwargs': run_kw, 'k': k, 'conv_int': conv_int}
+                    self.store(path=os.path.join(kwargs.get('int_dir', ''), name_base), name=f'{name_base}_{k}', mdl=model,
+                               objs=_objs)
             if I == N:
                 break
             if (early_stop is not None) and k == (early_stop - 1):

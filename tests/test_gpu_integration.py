@@ -73,3 +73,53 @@ def test_reference_plain_parareal_on_cuda_solver():
     solver = B.CudaSolverRK(ode.get_vector_field(), **cfg)
     out = B.CudaParareal(ode, solver, verbose='', **cfg).run(model='parareal', pool=B.CudaPool(), parall='mpi')
     assert out['k'] == 15 and out['conv_int'] == [1, 2, 3, 5, 8, 14, 17, 20, 26, 30, 33, 37, 40, 43, 50]
+
+
+def test_checkpoints_cross_the_boundary_in_both_directions(tmp_path):
+    """intermediate dumps (parareal.py:114-209, 420-431): (a) written by the REFERENCE driver running on the CUDA
+    backend and resumed by the reference's own load_int_dump; (b) the same dump resumed by this package's driver;
+    (c) a dump written by this package's driver resumed by the reference's load_int_dump.  All three end exactly
+    like the uninterrupted run."""
+    import pickle
+    from integration.cuda_backend import bind
+    from nearest_neighbors_gparareal_b200.checkpoint import load_dump
+    B = bind()
+    z, cfg, mkw = load_run("lorenz_N32_m11")
+    rk = {k: cfg[k] for k in ("Ng", "Nf", "F", "G")}
+
+    def ref_driver():
+        ode = B.Lorenz(normalization="-11")
+        return B.CudaParareal(ode, B.CudaSolverRK(ode.get_vector_field(), **rk), tspan=cfg["tspan"], N=cfg["N"],
+                              epsilon=float(z["epsilon"]), verbose='')
+
+    def pkg_driver():
+        ode = nn.Lorenz(normalization="-11")
+        return nn.Parareal(ode, nn.CudaSolverRK(ode.get_vector_field(), **rk), tspan=cfg["tspan"], N=cfg["N"],
+                           epsilon=float(z["epsilon"]), verbose='')
+
+    full = ref_driver().run(model='nngp', pool=B.CudaPool(), parall='mpi', **mkw)
+    K = full['k']
+    # (a) reference writes, reference resumes
+    part = ref_driver().run(model='nngp', pool=B.CudaPool(), parall='mpi', early_stop=3, store_int=True,
+                            int_dir=str(tmp_path), int_name='rf', **mkw)
+    assert part['k'] == 3
+    with open(tmp_path / 'rf' / 'rf_2', 'rb') as fh:
+        dump = pickle.load(fh)
+    assert isinstance(dump, B.ref.parareal.Parareal) and isinstance(dump.mdl, B.ref.models.NNGP_p)
+    pa = ref_driver()
+    ra = pa.load_int_dump(dump, ode=pa.ode, solver=pa.solver, pool=B.CudaPool(), early_stop=None, store_int=False)
+    assert ra['k'] == K and ra['conv_int'] == full['conv_int']
+    assert np.array_equal(ra['u'][:, :, K - 1], full['u'][:, :, K - 1])
+    # (b) reference writes, this package resumes
+    rb = pkg_driver().load_int_dump(load_dump(tmp_path / 'rf' / 'rf_2'), early_stop=None, store_int=False)
+    assert rb['k'] == K and rb['conv_int'] == full['conv_int']
+    assert np.array_equal(rb['u_last'], full['u'][:, :, K - 1])
+    # (c) this package writes, the reference resumes
+    pkg_driver().run(model='nngp', pool=nn.CudaPool(), parall='mpi', early_stop=3, store_int=True,
+                     int_dir=str(tmp_path), int_name='pk', **mkw)
+    with open(tmp_path / 'pk' / 'pk_2', 'rb') as fh:
+        dump_c = pickle.load(fh)
+    pc = ref_driver()
+    rc = pc.load_int_dump(dump_c, ode=pc.ode, solver=pc.solver, pool=B.CudaPool(), early_stop=None, store_int=False)
+    assert rc['k'] == K and rc['conv_int'] == full['conv_int']
+    assert np.array_equal(rc['u'][:, :, K - 1], full['u'][:, :, K - 1])

@@ -831,9 +831,9 @@ def test_more_than_32_neighbours(handle, n, d, m):
         want_f = onn.neg_log_lik(r2, y[oi, j], th_o, jit_o)
         want_p = onn.posterior_mean(r2, okq, y[oi, j], th_o, jit_o)
         assert np.isfinite(out["pred"][0, j])
-        if cond < 1e8 and np.isfinite(want_f):
+        if cond < 1e12 and np.isfinite(want_f):
             checked += 1
-            assert abs(out["fval_opt"][0, j] - want_f) <= 1e-8 * max(1.0, abs(want_f)), (j, cond)
+            assert abs(out["fval_opt"][0, j] - want_f) <= max(1e-8, 10 * cond * 2.2e-16) * max(1.0, abs(want_f)), (j, cond)
             assert abs(out["pred"][0, j] - want_p) <= max(1e-8, 4 * cond * 2.2e-16) * abs(want_p) + 1e-14, (j, cond)
     assert np.all(out["nfev"] >= 3) and np.all(out["nfev"] <= 400)
     print(f"m={m}: {same}/{total} searches on the oracle's trajectory, {checked}/{d} optima well conditioned")
