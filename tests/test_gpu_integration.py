@@ -113,7 +113,7 @@ def test_checkpoints_cross_the_boundary_in_both_directions(tmp_path):
     # (b) reference writes, this package resumes
     rb = pkg_driver().load_int_dump(load_dump(tmp_path / 'rf' / 'rf_2'), early_stop=None, store_int=False)
     assert rb['k'] == K and rb['conv_int'] == full['conv_int']
-    assert np.array_equal(rb['u_last'], full['u'][:, :, K - 1])
+    assert np.array_equal(rb['u'][:, :, K - 1], full['u'][:, :, K - 1])   # the reference returns u^0 .. u^{K-1}
     # (c) this package writes, the reference resumes
     pkg_driver().run(model='nngp', pool=nn.CudaPool(), parall='mpi', early_stop=3, store_int=True,
                      int_dir=str(tmp_path), int_name='pk', **mkw)
