@@ -295,7 +295,7 @@ def test_knn_ties_broken_by_index_and_edge_cases(handle):
     idx, dist = handle.knn_host(base[5][None], 3)
     assert dist[0, 0] == 0.0 and idx[0, 0] == 5
     with pytest.raises(_lib.NNGPError, match="outside"):
-        handle.knn_host(q[None], 33)
+        handle.knn_host(q[None], 161)
     with pytest.raises(_lib.NNGPError, match="fewer than m"):
         handle.knn_host(q[None], 9, n_rows=5)
     handle.dataset_reset()
