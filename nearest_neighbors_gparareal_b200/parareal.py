@@ -179,6 +179,9 @@ class Parareal():
                 raise Exception('A worker pool must be provided to run NNGP in parallel')
             kw = dict(kwargs)
             pool = kw.pop('pool')
+            if kw.get('nntype', 'nn') != 'nn':   # position-based neighbour rules (nnGPara_with_time.py:27-184)
+                from .models_alt import CudaNNGPAlt
+                return CudaNNGPAlt(n=self.n, N=self.N, worker_pool=pool, **kw)
             return CudaNNGP(n=self.n, N=self.N, worker_pool=pool, **kw)
         if name == 'gpjax':
             if 'pool' not in kwargs:
@@ -248,6 +251,13 @@ class Parareal():
             x = np.zeros((0, n))
             D = np.zeros((0, n))
             rec = RunHistory(N, n, cur['u'], cur['uG']) if store_int else None
+        cube = getattr(model, 'wants_data_cube', False)
+        if cube:  # data_x / data_D of parareal.py:243-247, only for the models that look observations up by position
+            data_x = np.full((N, n, N), np.nan)
+            data_D = np.full((N, n, N), np.nan)
+            if _load_mdl:
+                kk = _reload_objs['data_x'].shape[2]
+                data_x[:, :, :kk], data_D[:, :, :kk] = _reload_objs['data_x'], _reload_objs['data_D']
         k = max(k0 - 1, 0)
         for k in range(k0, N):
             if verbose == 'v':
@@ -281,7 +291,12 @@ class Parareal():
                 err[-1, k] = np.nextafter(eps, 0)
                 history.append(nxt['u'].copy())
                 break
-            model.fit_timed(x, D, k=k)
+            if cube:
+                data_x[I - 1:N, :, k] = cur['u'][I - 1:N]
+                data_D[I - 1:N, :, k] = cur['uF'][I:N + 1] - cur['uG'][I:N + 1]
+                model.fit_timed(x, D, k=k, data_x=data_x, data_y=data_D)
+            else:
+                model.fit_timed(x, D, k=k)
             # serial sweep (parareal.py:359-382)
             for i in range(I, N):
                 nxt['uG'][i + 1], secs = solver.run_G_timed(t[i], t[i + 1], nxt['u'][i])

@@ -316,3 +316,32 @@ def test_device_driver_checkpoints_in_reference_layout_and_resume(tmp_path):
     assert res['k'] == full['k'] and res['conv_int'] == full['conv_int']
     assert np.array_equal(res['u_last'], full['u'])
     assert np.array_equal(res['err'], full['err'], equal_nan=True)
+
+
+# nnGPara_with_time.py:27-184, published in `nngptime_diff_subsets2` (nn=16, eps=5e-7): K per neighbour rule
+PUBLISHED_NNTYPE_K = {"fhn": {'nn': 5, 'col+rnd': 8, 'col_only': 8, 'row_col': 8, 'row': 10, 'col_full': 7},
+                      "lorenz": {'nn': 10, 'col+rnd': 13, 'col_only': 13, 'row_col': 13, 'row': 12, 'col_full': 13}}
+
+
+@pytest.mark.parametrize("system", ["fhn", "lorenz"])
+def test_position_based_neighbour_rules_against_published_K(system):
+    """the six neighbour rules of the reference's time-aware study: 'nn' is the standard model (bitwise), the
+    position-based ones converge within two iterations of the published counts (different random fill-ups and
+    argsort tie orders across NumPy versions move 'col+rnd' and 'row_col' by an iteration)"""
+    mk = {"fhn": lambda: nn.FHN_ODE(normalization='-11'), "lorenz": lambda: nn.Lorenz(normalization='-11')}[system]
+    got = {}
+    for nntype, Kpub in PUBLISHED_NNTYPE_K[system].items():
+        ode = mk()
+        cfg = nn.Config(ode).get()
+        solver = nn.CudaSolverRK(ode.get_vector_field(), **cfg)
+        p = nn.Parareal(ode, solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=5e-7, verbose='')
+        out = p.run(model='nngp', pool=nn.CudaPool(), parall='mpi', nn=16, nntype=nntype, seed=45)
+        got[nntype] = out['k']
+        assert out['converged'], nntype
+        if nntype == 'nn':
+            ref = nn.Parareal(mk(), solver, tspan=cfg["tspan"], N=cfg["N"], epsilon=5e-7, verbose='').run(
+                model='nngp', pool=nn.CudaPool(), parall='mpi', nn=16, seed=45)
+            assert np.array_equal(ref['u_last'], out['u_last'])
+    print(f"{system}: K per neighbour rule {got} (published {PUBLISHED_NNTYPE_K[system]})")
+    for nntype, Kpub in PUBLISHED_NNTYPE_K[system].items():
+        assert abs(got[nntype] - Kpub) <= 2, (nntype, got[nntype], Kpub)

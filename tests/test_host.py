@@ -358,3 +358,57 @@ def test_lockstep_nelder_mead_equals_scipy_bit_for_bit():
                     ref = minimize(f, x0, method='Nelder-Mead', options={'fatol': tol, 'xatol': tol})
                 assert nm.fcalls == ref.nfev, (f.__name__, x0, nm.fcalls, ref.nfev)
                 assert np.array_equal(x, ref.x) and (fv == ref.fun or (np.isinf(fv) and np.isinf(ref.fun)))
+
+
+def test_position_based_neighbour_rules_pick_the_documented_rows():
+    """models_alt.CudaNNGPAlt.neighbour_rows against a direct transcription of the generators of
+    nnGPara_with_time.py:98-171 on a synthetic observation cube (no device call)"""
+    from nearest_neighbors_gparareal_b200.models_alt import CudaNNGPAlt
+    rng = np.random.default_rng(0)
+    N, n, k = 12, 2, 3
+    first = [0, 1, 3, 4]                      # first unconverged slice per iteration
+    data_x = np.full((N, n, N), np.nan)
+    rows = []
+    for j in range(k + 1):
+        for s in range(first[j], N):
+            data_x[s, :, j] = rng.standard_normal(n)
+            rows.append(data_x[s, :, j].copy())
+    x = np.array(rows)
+
+    def ref_cycle(mtx, it, sl, by_row):
+        def cyc(a, b):
+            done_a = False
+            while True:
+                try:
+                    yield next(a)
+                except StopIteration:
+                    done_a = True
+                try:
+                    yield next(b)
+                except StopIteration:
+                    if done_a:
+                        break
+        if by_row:   # 'row': iterations outermost
+            for row in range(it, -1, -1):
+                for col in cyc(iter(range(sl, -1, -1)), iter(range(sl + 1, mtx.shape[0]))):
+                    if not np.any(np.isnan(mtx[col, :, row])):
+                        yield mtx[col, :, row]
+        else:        # 'col_full': slices outermost
+            for col in cyc(iter(range(sl, -1, -1)), iter(range(sl + 1, mtx.shape[0]))):
+                for row in range(it, -1, -1):
+                    if not np.any(np.isnan(mtx[col, :, row])):
+                        yield mtx[col, :, row]
+
+    for nntype, by_row in (('row', True), ('col_full', False)):
+        m = CudaNNGPAlt.__new__(CudaNNGPAlt)
+        m.nntype, m.nn, m.k, m.x, m.data_x = nntype, 7, k, x, data_x
+        present = ~np.isnan(data_x[:, 0, :k + 1])
+        m._present = present
+        m._first = np.array(first)
+        m._offset = np.concatenate([[0], np.cumsum(N - m._first)])[:k + 1]
+        for i in (4, 7, 11):
+            gen = ref_cycle(data_x[:, :, :k + 1], k, i, by_row)
+            want = np.array([next(gen) for _ in range(7)])
+            assert np.array_equal(x[m.neighbour_rows(i)], want), (nntype, i)
+    m.nntype = 'col_only'
+    assert np.array_equal(x[m.neighbour_rows(6)], data_x[6, :, :k + 1].T)
