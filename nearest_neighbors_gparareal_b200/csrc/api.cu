@@ -160,8 +160,8 @@ int nngp_create(int device, nngp_handle_t* out) {
   if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMalloc(&h->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
-      cudaMemset(h->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) {
+      cudaMalloc(&h->d_ticket, 8 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->d_ticket, 0, 8 * sizeof(unsigned int)) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "nngp_create: auxiliary stream / events failed");
   }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 static constexpr int KNN_SEL_THREADS = 256;
 
@@ -296,7 +297,7 @@ __device__ __forceinline__ void select_topm_cta(const double* __restrict__ dq, c
     const long long i0 = lo + (long long)w * 32 + lane;
     if (i0 < hi) {
       cn = __ldcg(dq + i0);
-      cnidx = iq ? iq[i0] : i0;
+      cnidx = iq ? __ldcg(iq + i0) : i0;
     }
   }
   for (long long base = lo + (long long)w * 32; base < hi; base += NT) {
@@ -308,7 +309,7 @@ __device__ __forceinline__ void select_topm_cta(const double* __restrict__ dq, c
       cnidx = IMAX;
       if (i1 < hi) {
         cn = __ldcg(dq + i1);
-        cnidx = iq ? iq[i1] : i1;
+        cnidx = iq ? __ldcg(iq + i1) : i1;
       }
     }
     const double td = shfl_d(bd, m - 1);
@@ -386,28 +387,35 @@ select_kernel(const double* __restrict__ dist, const long long* __restrict__ in_
 }
 
 // ---------------------------------------------------------------------------------------
-// Sweep prologue of one slice in ONE launch (was: distance scan, selection, neighbour matrix = three
-// dependent launches of 35 + 24 + 26 us): every CTA scans 256 dataset rows for the single query; the CTA that
-// finishes last (ticket counter) selects the m nearest rows over all distances and forms the m x m matrix of
-// squared distances between them (the r2 of the GP kernels, cdist arithmetic).  n <= KNN_CHUNK rows.
+// Few queries (the sweep: one): distance scan, top-m selection and -- for the sweep -- the neighbour matrix in ONE
+// launch (was three dependent launches, 35 + 24 + 26 us in the sweep; at n = 65 536 the scan ran at 90 % of HBM but the
+// call at 40 %).  Grid (chunks of 256 rows, queries).  Every CTA scans its 256 rows, selects their m best (level 1,
+// in parallel on all SMs) and writes m candidates; the CTA that finishes last for its query (ticket counter) merges
+// the candidates (level 2) and, when r2 is given, forms the m x m squared-distance matrix of the selected rows (the
+// r2 of the GP kernels, cdist arithmetic).
 // ---------------------------------------------------------------------------------------
 static constexpr int PRO_THREADS = 256;
 static constexpr int PRO_JC = 64;
 
 template <int PF>
 __global__ void __launch_bounds__(PRO_THREADS)
-sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ X, long long cap, long long n, int d,
-                      const double* __restrict__ q, int m, double* __restrict__ dist_all, unsigned int* ticket,
-                      long long* __restrict__ idx_out, double* __restrict__ dist_out, double* __restrict__ r2) {
+scan_select_kernel(const double* __restrict__ XT, const double* __restrict__ X, long long cap, long long n, int d,
+                   const double* __restrict__ Q, int m, double* __restrict__ dist_all, double* __restrict__ cand_d,
+                   long long* __restrict__ cand_i, unsigned int* tickets, long long* __restrict__ idx_out,
+                   double* __restrict__ dist_out, double* __restrict__ r2) {
   extern __shared__ double qs[];  // [d]
   constexpr int NW = PRO_THREADS / 32;
   __shared__ double cd[NW * 32];
   __shared__ long long ci[NW * 32];
   __shared__ double tile[NNGP_MAX_NEIGHBOURS][PRO_JC + 1];
   __shared__ bool last;
+  const int qi = blockIdx.y;
+  const double* q = Q + (long long)qi * d;
+  double* dq = dist_all + (long long)qi * n;
   for (int e = threadIdx.x; e < d; e += blockDim.x) qs[e] = q[e];
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long lo = (long long)blockIdx.x * PRO_THREADS, hi = min(n, lo + PRO_THREADS);
+  const long long i = lo + threadIdx.x;
   if (i < n) {
     const double* xp = XT + i;
     double acc = 0.0;
@@ -433,17 +441,27 @@ sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ 
       const double diff = qs[j] - xp[(long long)j * cap];
       acc = acc + diff * diff;
     }
-    __stcg(dist_all + i, acc);
+    __stcg(dq + i, acc);
   }
+  __syncthreads();  // the CTA's distances are visible to the CTA (global writes + barrier)
+  // level 1: the m best of this CTA's rows
+  const long long cbase = ((long long)qi * gridDim.x + blockIdx.x) * m;
+  select_topm_cta<NW>(dq, nullptr, lo, hi, m, cand_i + cbase, cand_d + cbase, cd, ci);
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(tickets + qi, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
-  select_topm_cta<NW>(dist_all, nullptr, 0, n, m, idx_out, dist_out, cd, ci);
+  // level 2: merge the candidates of all CTAs of this query
+  const long long nc = (long long)gridDim.x * m;
+  long long* io = idx_out + (long long)qi * m;
+  select_topm_cta<NW>(cand_d + (long long)qi * nc, cand_i + (long long)qi * nc, 0, nc, m, io, dist_out + (long long)qi * m,
+                      cd, ci);
+  if (threadIdx.x == 0) tickets[qi] = 0;  // ready for the next launch
+  if (r2 == nullptr) return;
   __syncthreads();  // idx_out written by warp 0 of this CTA
-  // neighbour matrix: r2[a][b] = ||x_a - x_b||^2, strict left-to-right sums
+  double* r2q = r2 + (long long)qi * m * m;
   const int npairs = m * (m + 1) / 2;
   constexpr int PP = (NNGP_MAX_NEIGHBOURS * (NNGP_MAX_NEIGHBOURS + 1) / 2 + PRO_THREADS - 1) / PRO_THREADS;
   int pa[PP], pb[PP];
@@ -467,7 +485,7 @@ sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ 
     __syncthreads();
     for (int e = threadIdx.x; e < m * PRO_JC; e += PRO_THREADS) {
       const int r = e / PRO_JC, jj = e - r * PRO_JC;
-      if (jj < jn) tile[r][jj] = X[__ldcg(idx_out + r) * d + j0 + jj];
+      if (jj < jn) tile[r][jj] = X[__ldcg(io + r) * d + j0 + jj];
     }
     __syncthreads();
 #pragma unroll
@@ -485,13 +503,11 @@ sweep_prologue_kernel(const double* __restrict__ XT, const double* __restrict__ 
 #pragma unroll
   for (int u = 0; u < PP; u++) {
     if (threadIdx.x + u * PRO_THREADS < npairs) {
-      r2[pa[u] * m + pb[u]] = acc2[u];
-      r2[pb[u] * m + pa[u]] = acc2[u];
+      r2q[pa[u] * m + pb[u]] = acc2[u];
+      r2q[pb[u] * m + pa[u]] = acc2[u];
     }
   }
-  if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch
 }
-
 
 // m > 32 (rare: nn='adaptive' past iteration 30): m passes of "smallest key above the last one" by one CTA per query
 __global__ void __launch_bounds__(256)
@@ -551,12 +567,31 @@ static long long knn_chunk_rows(int nq, long long n) {
 static inline size_t knn_pad256(size_t b) { return ((b + 255) / 256) * 256; }
 
 // [distances nq*n | per-chunk candidate distances nq*chunks*m | candidate indices]
+static constexpr int KNN_FUSED_MAX_Q = 4;  // queries per call served by scan_select_kernel (one ticket each)
+
 size_t knn_workspace_bytes(int nq, long long n, int m) {
   const long long cr = knn_chunk_rows(nq, n);
-  const size_t chunks = (size_t)((n + cr - 1) / cr);
+  size_t chunks = (size_t)((n + cr - 1) / cr);
+  if (nq <= KNN_FUSED_MAX_Q) chunks = (size_t)((n + PRO_THREADS - 1) / PRO_THREADS);
   size_t b = knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
-  if (chunks > 1) b += 2 * knn_pad256(sizeof(double) * (size_t)nq * chunks * (size_t)m);
+  if (chunks > 1 || nq <= KNN_FUSED_MAX_Q) b += 2 * knn_pad256(sizeof(double) * (size_t)nq * chunks * (size_t)m);
   return b;
+}
+
+// distance scan + top-m (+ neighbour matrix when d_r2 is given) of up to KNN_FUSED_MAX_Q queries in one launch
+static int scan_select_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n, long long* d_idx,
+                              double* d_dist, double* d_r2, void* ws, cudaStream_t st) {
+  const int d = h->ds_d;
+  const unsigned chunks = (unsigned)((n + PRO_THREADS - 1) / PRO_THREADS);
+  double* dist = (double*)ws;
+  char* base = (char*)ws + knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
+  double* cand_d = (double*)base;
+  long long* cand_i = (long long*)(base + knn_pad256(sizeof(double) * (size_t)nq * chunks * m));
+  scan_select_kernel<16><<<dim3(chunks, nq), PRO_THREADS, (size_t)d * sizeof(double), st>>>(
+      h->ds_xt, h->ds_x, h->ds_cap, n, d, d_q, m, dist, cand_d, cand_i, h->d_ticket, d_idx, d_dist, d_r2);
+  h->launches++;
+  NNGP_CUDA(h, cudaGetLastError());
+  return 0;
 }
 
 int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
@@ -570,6 +605,9 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
   const int d = h->ds_d;
   double* dist = (double*)ws;
   ProfScope prof(h, 1, st);
+  if (nq <= KNN_FUSED_MAX_Q && m <= NNGP_MAX_NEIGHBOURS && (size_t)d * sizeof(double) <= 48 * 1024 &&
+      getenv("NNGP_KNN_NO_FUSED") == nullptr)
+    return scan_select_launch(h, d_q, nq, m, n, d_idx, d_dist, nullptr, ws, st);
   const int tb = 128;
   const unsigned gx = (unsigned)((n + tb - 1) / tb);
   const size_t qrow = (size_t)d * sizeof(double), lim = 48 * 1024;
@@ -610,18 +648,12 @@ int knn_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n_ro
 
 // scan + selection + neighbour matrix of ONE query in one launch; false when the shape needs the general path
 bool knn_prep_fused_ok(nngp_handle_t h, long long n, int m) {
-  return m <= NNGP_MAX_NEIGHBOURS && n <= KNN_CHUNK && n >= m && (size_t)h->ds_d * sizeof(double) <= 48 * 1024;
+  return m <= NNGP_MAX_NEIGHBOURS && n >= m && (size_t)h->ds_d * sizeof(double) <= 48 * 1024;
 }
 
 int knn_prep_fused_launch(nngp_handle_t h, const double* d_q, int m, long long n, long long* d_idx, double* d_dist,
                           double* d_r2, void* ws, unsigned int* ticket, cudaStream_t st) {
-  const int d = h->ds_d;
-  double* dist = (double*)ws;
+  (void)ticket;
   ProfScope prof(h, 1, st);
-  const unsigned g = (unsigned)((n + PRO_THREADS - 1) / PRO_THREADS);
-  sweep_prologue_kernel<16><<<g, PRO_THREADS, (size_t)d * sizeof(double), st>>>(h->ds_xt, h->ds_x, h->ds_cap, n, d, d_q, m,
-                                                                             dist, ticket, d_idx, d_dist, d_r2);
-  h->launches++;
-  NNGP_CUDA(h, cudaGetLastError());
-  return 0;
+  return scan_select_launch(h, d_q, 1, m, n, d_idx, d_dist, d_r2, ws, st);
 }
