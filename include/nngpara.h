@@ -154,6 +154,10 @@ double nngp_get_pivot_guard(nngp_handle_t h);
  * search per warp, 2 several searches per warp (32 / (m/2)).  Results are bit-identical; only the speed differs
  * (DESIGN.md section 4.5).  Environment override at nngp_create: NNGP_FIT_MODE=auto|warp|grouped.              */
 int nngp_set_fit_mode(nngp_handle_t h, int mode);
+/* One-search-per-warp kernel only: a search still running after `evaluations` objective evaluations (default 100; 0 = never)
+ * is continued by a second kernel in which the four warps of a CTA evaluate the candidate points of a Nelder-Mead iteration
+ * side by side -- same decisions and bits, half the serial latency of the searches that end a launch.  NNGP_FIT_BUDGET. */
+int nngp_set_fit_budget(nngp_handle_t h, int evaluations);
 
 /* ---- fused on-device sweep: parareal.py:359-382 for slices i = I..N-1 -------------------
  * per slice: uG_next[i+1] = G(t_i, t_{i+1}, u_next[i]); kNN of u_next[i]; fit+predict;

@@ -60,6 +60,7 @@ SIGNATURES = {
     "nngp_set_pivot_guard": (ci, [vp, cd]),
     "nngp_get_pivot_guard": (cd, [vp]),
     "nngp_set_fit_mode": (ci, [vp, ci]),
+    "nngp_set_fit_budget": (ci, [vp, ci]),
     "nngp_counters": (ci, [vp, c_ll_p, c_ll_p, ci]),
     "nngp_profile_enable": (ci, [vp, ci]),
     "nngp_profile_read": (ci, [vp, vp, vp, ci]),
@@ -306,6 +307,10 @@ class Handle:
     def set_fit_mode(self, mode):
         """'auto' | 'warp' (one search per warp) | 'grouped' (several searches per warp); same bits either way"""
         self.check(self.lib.nngp_set_fit_mode(self.h, {"auto": 0, "warp": 1, "grouped": 2}[mode]))
+
+    def set_fit_budget(self, evaluations):
+        """evaluations after which a search moves to the four-warp continuation kernel (0: never); same bits"""
+        self.check(self.lib.nngp_set_fit_budget(self.h, int(evaluations)))
 
     def get_pivot_guard(self):
         return float(self.lib.nngp_get_pivot_guard(self.h))

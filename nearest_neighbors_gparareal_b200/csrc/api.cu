@@ -43,12 +43,15 @@ ProfScope::~ProfScope() {
 }
 
 // a zeroed task-queue head for the next fit launch on stream st (slots are re-zeroed in bulk)
+// (a fit uses up to three counters: its task queue, the number of parked long searches and their queue)
 static unsigned int* next_queue(nngp_handle_t h, cudaStream_t st) {
-  if (h->queue_next >= NNGP_QUEUE_SLOTS) {
+  if (h->queue_next + 4 > NNGP_QUEUE_SLOTS) {
     cudaMemsetAsync(h->d_queues, 0, NNGP_QUEUE_SLOTS * sizeof(unsigned int), st);
     h->queue_next = 0;
   }
-  return h->d_queues + h->queue_next++;
+  unsigned int* p = h->d_queues + h->queue_next;
+  h->queue_next += 4;
+  return p;
 }
 
 // the fit kernel leaves its completion counters zero; they only need clearing when they move
@@ -148,6 +151,7 @@ int nngp_create(int device, nngp_handle_t* out) {
   h->sm_count = prop.multiProcessorCount;
   if (const char* fm = getenv("NNGP_FIT_MODE")) h->fit_mode = (strcmp(fm, "warp") == 0) ? 1 : (strcmp(fm, "grouped") == 0) ? 2 : 0;
   if (getenv("NNGP_FIT_LEGACY")) h->fit_mode = 1;
+  if (const char* b = getenv("NNGP_FIT_BUDGET")) h->fit_budget = atoi(b);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return nngp_fail(nullptr, "cudaStreamCreate failed");
@@ -233,6 +237,12 @@ int nngp_set_pivot_guard(nngp_handle_t h, double ulps) {
 int nngp_set_fit_mode(nngp_handle_t h, int mode) {
   if (mode < 0 || mode > 2) return nngp_fail(h, "set_fit_mode: mode=%d outside {0 auto, 1 warp, 2 grouped}", mode);
   h->fit_mode = mode;
+  return 0;
+}
+
+int nngp_set_fit_budget(nngp_handle_t h, int evaluations) {
+  if (evaluations < 0 || evaluations > 400) return nngp_fail(h, "set_fit_budget: %d outside [0, 400]", evaluations);
+  h->fit_budget = evaluations;
   return 0;
 }
 

@@ -583,6 +583,12 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
 struct NMOut {
   double x0, x1, f;
   int nfev;
+  // budget > 0 and the search was still running after `budget` evaluations at the start of an iteration: the sorted
+  // simplex is handed to gp_fit_spec_kernel, which continues it with the candidate points of an iteration evaluated
+  // side by side on the four warps of a CTA
+  bool unfinished;
+  double sx[3][2], sf[3];
+  int it;
 };
 
 __device__ __forceinline__ void sort3(double (&sx)[3][2], double (&sf)[3]) {
@@ -609,8 +615,10 @@ __device__ __forceinline__ double shrink_to(double x0, double xj) {
 template <int M>
 __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10, double fatol, double xatol,
                                              const PairSlots<M>& P, double y, int m, int lane,
-                                             double* __restrict__ Lt, double hml, bool head_batch, double guard) {
+                                             double* __restrict__ Lt, double hml, bool head_batch, double guard,
+                                             int budget = 0) {
   const int maxfun = 400, maxiter = 400;  // 200 * N
+  bool unfinished = false;
   double sx[3][2], sf[3];
   sx[0][0] = s0; sx[0][1] = s1;
   sx[1][0] = (s0 != 0.0) ? __dmul_rn(1.05, s0) : 0.00025; sx[1][1] = s1;
@@ -723,6 +731,10 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
     xr1 = __dsub_rn(__dmul_rn(2.0, xb1), sx[2][1]);
     phase = PH_REFLECT; p0 = xr0; p1 = xr1;
     cmask = 0;
+    if (budget > 0 && fcalls >= budget) {  // iteration boundary: sorted simplex, nothing pending
+      unfinished = true;
+      break;
+    }
     if (head_batch && sf[0] == dinf()) {  // sorted: the best vertex is +inf, so all are
       cx0[0] = xr0; cx1[0] = xr1;
       cx0[1] = __dadd_rn(__dmul_rn(0.5, xb0), __dmul_rn(0.5, sx[2][0]));  // inside contraction
@@ -740,6 +752,14 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
   o.x1 = sx[0][1];
   o.f = fmin(fmin(sf[0], sf[1]), sf[2]);
   o.nfev = fcalls;
+  o.unfinished = unfinished;
+  o.it = it;
+#pragma unroll
+  for (int v = 0; v < 3; v++) {
+    o.sx[v][0] = sx[v][0];
+    o.sx[v][1] = sx[v][1];
+    o.sf[v] = sf[v];
+  }
   return o;
 }
 
@@ -771,6 +791,13 @@ struct FitArgs {
   long long ld_pred;      // row stride of pred / add
   double fatol, xatol;
   double guard;           // failed-pivot threshold relative to the diagonal (ulps * 2^-52)
+  // long searches: after `budget` evaluations a search parks its simplex in saves[task] (12 doubles) and its id in
+  // cont_list[atomicAdd(cont_count)]; gp_fit_spec_kernel continues them (queue2 hands them out)
+  int budget;
+  double* saves;
+  int* cont_list;
+  unsigned int* cont_count;
+  unsigned int* queue2;
 };
 
 template <int M>
@@ -785,6 +812,73 @@ __device__ __noinline__ double posterior_mean(double th0, double th1, double jit
 
 #include "gpfit_group.cuh"
 #include "gpfit_big.cuh"
+
+// results of a finished search; the warp that completes the last search of its (query, dimension) applies the selection
+// rule (models.py:212-215) and computes the posterior mean (models.py:162-168)
+template <int M>
+__device__ __forceinline__ void finish_search(const FitArgs& A, int task, double x0, double x1, double f, int nfev,
+                                              const PairSlots<M>& P, double y, int lane, double* Lt) {
+  const int m = A.m, d = A.d, R = A.R, nruns = NNGP_N_JITTER * R;
+  const int qj = task / nruns, run = task - qj * nruns;
+  const int q = qj / A.dl, j = A.j0 + (qj - q * A.dl);
+  const long long gqj = (long long)q * d + j, gtask = gqj * nruns + run;
+  unsigned int prior = 0;
+  if (lane == 0) {
+    A.res[(long long)task * 3] = f;
+    A.res[(long long)task * 3 + 1] = x0;
+    A.res[(long long)task * 3 + 2] = x1;
+    atomicAdd(A.counters, 1ULL);
+    atomicAdd(A.counters + 1, (unsigned long long)nfev);
+    if (A.nfev) A.nfev[gtask] = nfev;
+    if (A.fvals) A.fvals[gtask] = f;
+    if (A.thetas) {
+      A.thetas[gtask * 2] = x0;
+      A.thetas[gtask * 2 + 1] = x1;
+    }
+    __threadfence();
+    prior = atomicAdd(A.done + qj, 1u);
+  }
+  prior = __shfl_sync(FULL, prior, 0);
+  if (prior != (unsigned)(nruns - 1)) return;
+  // this warp finished the last search of (q, j): selection + posterior mean
+  __threadfence();
+  const volatile double* rf = A.res + (long long)qj * nruns * 3;
+  double fmin_all = rf[0];
+  for (int r = 1; r < nruns; r++) {
+    const double v = rf[3 * r];
+    fmin_all = (v < fmin_all) ? v : fmin_all;
+  }
+  const double thr = fmin_all * 0.9;
+  bool any = false;
+  for (int r = 0; r < nruns; r++) any |= (rf[3 * r] < thr);
+  int best = -1;
+  double fb = 0.0;
+  for (int r = 0; r < nruns; r++) {
+    const double v = rf[3 * r];
+    if (any && !(v < thr)) continue;
+    if (best < 0 || v < fb) {
+      best = r;
+      fb = v;
+    }
+  }
+  const int ab = best / R;
+  const double th0 = rf[3 * best + 1], th1 = rf[3 * best + 2];
+  const double kq = (lane < m) ? A.dist[(long long)q * m + lane] : 0.0;
+  double mean = posterior_mean<M>(th0, th1, c_jit10[ab], P, y, kq, m, lane, Lt, A.guard);
+  __syncwarp();
+  if (lane == 0) {
+    A.done[qj] = 0;  // leave the counters clean for the next launch
+    const long long op = (long long)q * A.ld_pred + j;
+    if (A.add) mean = mean + A.add[op];
+    A.pred[op] = mean;
+    if (A.theta_opt) {
+      A.theta_opt[gqj * 2] = th0;
+      A.theta_opt[gqj * 2 + 1] = th1;
+    }
+    if (A.jitter_opt) A.jitter_opt[gqj] = (double)(ab - 20);
+    if (A.fval_opt) A.fval_opt[gqj] = fb;
+  }
+}
 
 // registers per thread: 4-warp CTAs, K CTAs per SM
 #ifndef FIT_OCC20
@@ -825,64 +919,141 @@ gp_fit_predict_kernel(FitArgs A) {
     const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
     const signed char* st = A.starts + gtask * 2;
     const NMOut o = nelder_mead<M>((double)st[0], (double)st[1], c_jit10[a], A.fatol, A.xatol, P, y, m,
-                                   lane, Lt, hml, A.head_batch != 0, A.guard);
-    unsigned int prior = 0;
-    if (lane == 0) {
-      A.res[(long long)task * 3] = o.f;
-      A.res[(long long)task * 3 + 1] = o.x0;
-      A.res[(long long)task * 3 + 2] = o.x1;
-      atomicAdd(A.counters, 1ULL);
-      atomicAdd(A.counters + 1, (unsigned long long)o.nfev);
-      if (A.nfev) A.nfev[gtask] = o.nfev;
-      if (A.fvals) A.fvals[gtask] = o.f;
-      if (A.thetas) {
-        A.thetas[gtask * 2] = o.x0;
-        A.thetas[gtask * 2 + 1] = o.x1;
+                                   lane, Lt, hml, A.head_batch != 0, A.guard, A.budget);
+    if (o.unfinished) {
+      if (lane == 0) {
+        double* sv = A.saves + (long long)task * 12;
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+          sv[2 * v] = o.sx[v][0];
+          sv[2 * v + 1] = o.sx[v][1];
+          sv[6 + v] = o.sf[v];
+        }
+        sv[9] = (double)o.it;
+        sv[10] = (double)o.nfev;
+        A.cont_list[atomicAdd(A.cont_count, 1u)] = task;
       }
-      __threadfence();
-      prior = atomicAdd(A.done + qj, 1u);
+      continue;
     }
-    prior = __shfl_sync(FULL, prior, 0);
-    if (prior != (unsigned)(nruns - 1)) continue;
-    // this warp finished the last search of (q, j): selection + posterior mean
-    __threadfence();
-    const volatile double* rf = A.res + (long long)qj * nruns * 3;
-    // models.py:212-215: mask = fval < 0.9*min; empty mask -> all; first minimum in task order
-    double fmin_all = rf[0];
-    for (int r = 1; r < nruns; r++) {
-      const double v = rf[3 * r];
-      fmin_all = (v < fmin_all) ? v : fmin_all;
+    finish_search<M>(A, task, o.x0, o.x1, o.f, o.nfev, P, y, lane, Lt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Continuation of the long searches.  A launch lasts as long as its longest serial chain of objective evaluations
+// (at the FHN target: a handful of searches with 200-300 evaluations of ~3 300 cycles each, and -- when the fits of a
+// predict are sharded over 8 GPUs -- nothing else to hide them behind).  gp_fit_predict_kernel parks every search
+// that is still running after `budget` evaluations; here ONE CTA continues one search and its four warps evaluate,
+// side by side, the points the iteration can ask for: reflection, expansion, outside and inside contraction (all
+// vertices +inf: reflection, inside contraction and the two shrunk vertices).  The Nelder-Mead state machine
+// (nm_step) then consumes the values in SciPy's order, so decisions, evaluation counts and results are bit-identical
+// to the sequential search; an iteration costs one evaluation latency instead of two (four when it shrinks).
+// ---------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(GP_WARPS * 32, FitOcc<M>::value)
+gp_fit_spec_kernel(FitArgs A) {
+  static_assert(GP_WARPS == 4, "four candidate points per iteration");
+  extern __shared__ double sm[];
+  __shared__ double s_f[GP_WARPS];
+  __shared__ int s_task;
+  const int m = A.m, d = A.d, R = A.R, nruns = NNGP_N_JITTER * R;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* Lt = sm + w * (M * (M + 2));
+  const double hml = (m / 2.0) * 1.8378770664093453;
+  PairSlots<M> P;
+  pair_slots_init<M>(P, lane, m);
+  int q_loaded = -1;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const unsigned pos = atomicAdd(A.queue2, 1u);
+      s_task = (pos < *A.cont_count) ? A.cont_list[pos] : -1;
     }
-    const double thr = fmin_all * 0.9;
-    bool any = false;
-    for (int r = 0; r < nruns; r++) any |= (rf[3 * r] < thr);
-    int best = -1;
-    double fb = 0.0;
-    for (int r = 0; r < nruns; r++) {
-      const double v = rf[3 * r];
-      if (any && !(v < thr)) continue;
-      if (best < 0 || v < fb) {
-        best = r;
-        fb = v;
+    __syncthreads();
+    const int task = s_task;
+    __syncthreads();
+    if (task < 0) break;
+    const int qj = task / nruns, run = task - qj * nruns;
+    const int q = qj / A.dl, j = A.j0 + (qj - q * A.dl);
+    const double jit10 = c_jit10[run / R];
+    if (q != q_loaded) {
+      pair_slots_load<M>(P, A.r2 + (long long)q * m * m, m);
+      q_loaded = q;
+    }
+    const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
+    NMState S;
+    nm_init(S, -1.0, -1.0);
+    {
+      const double* sv = A.saves + (long long)task * 12;
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        S.sx[v][0] = sv[2 * v];
+        S.sx[v][1] = sv[2 * v + 1];
+        S.sf[v] = sv[6 + v];
+      }
+      S.it = (int)sv[9];
+      S.fcalls = (int)sv[10];
+      // the start of an iteration, as nelder_mead / nm_step leave it
+      S.xb0 = __dmul_rn(__dadd_rn(S.sx[0][0], S.sx[1][0]), 0.5);
+      S.xb1 = __dmul_rn(__dadd_rn(S.sx[0][1], S.sx[1][1]), 0.5);
+      S.xr0 = __dsub_rn(__dmul_rn(2.0, S.xb0), S.sx[2][0]);
+      S.xr1 = __dsub_rn(__dmul_rn(2.0, S.xb1), S.sx[2][1]);
+      S.phase = PH_REFLECT;
+      S.p0 = S.xr0;
+      S.p1 = S.xr1;
+    }
+    bool fin = false;
+    while (!fin) {
+      double c0[4], c1[4], fc[4];
+      int navail = 4;
+      const double w0 = S.sx[2][0], w1 = S.sx[2][1];
+      c0[0] = S.xr0; c1[0] = S.xr1;
+      if (S.sf[0] == dinf()) {  // every vertex +inf: reflection, inside contraction, the two shrunk vertices
+        c0[1] = __dadd_rn(__dmul_rn(0.5, S.xb0), __dmul_rn(0.5, w0)); c1[1] = __dadd_rn(__dmul_rn(0.5, S.xb1), __dmul_rn(0.5, w1));
+        c0[2] = shrink_to(S.sx[0][0], S.sx[1][0]); c1[2] = shrink_to(S.sx[0][1], S.sx[1][1]);
+        c0[3] = shrink_to(S.sx[0][0], w0); c1[3] = shrink_to(S.sx[0][1], w1);
+      } else {                  // reflection, expansion, outside contraction, inside contraction
+        c0[1] = __dsub_rn(__dmul_rn(3.0, S.xb0), __dmul_rn(2.0, w0)); c1[1] = __dsub_rn(__dmul_rn(3.0, S.xb1), __dmul_rn(2.0, w1));
+        c0[2] = __dsub_rn(__dmul_rn(1.5, S.xb0), __dmul_rn(0.5, w0)); c1[2] = __dsub_rn(__dmul_rn(1.5, S.xb1), __dmul_rn(0.5, w1));
+        c0[3] = __dadd_rn(__dmul_rn(0.5, S.xb0), __dmul_rn(0.5, w0)); c1[3] = __dadd_rn(__dmul_rn(0.5, S.xb1), __dmul_rn(0.5, w1));
+      }
+      {
+        const double f = gp_core<M, false>(c0[w], c1[w], jit10, P, y, m, lane, Lt, hml, A.guard).val;
+        if (lane == 0) s_f[w] = f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < 4; v++) fc[v] = s_f[v];
+      __syncthreads();
+      for (;;) {  // consume in the order the state machine asks (uniform over the CTA: every warp holds the same state)
+        int hit = -1;
+#pragma unroll
+        for (int v = 3; v >= 0; v--)
+          if (v < navail && S.p0 == c0[v] && S.p1 == c1[v]) hit = v;
+        if (hit < 0) {
+          // not among the evaluated points (a shrink after a finite contraction): evaluate it now -- and the second
+          // shrunk vertex with it, which the state machine will ask for next
+          c0[0] = S.p0; c1[0] = S.p1;
+          const bool two = (S.phase == PH_SHRINK1);
+          c0[1] = two ? shrink_to(S.sx[0][0], S.sx[2][0]) : S.p0;
+          c1[1] = two ? shrink_to(S.sx[0][1], S.sx[2][1]) : S.p1;
+          navail = 2;
+          if (w < 2) {
+            const double f = gp_core<M, false>(c0[w], c1[w], jit10, P, y, m, lane, Lt, hml, A.guard).val;
+            if (lane == 0) s_f[w] = f;
+          }
+          __syncthreads();
+          fc[0] = s_f[0];
+          fc[1] = s_f[1];
+          __syncthreads();
+          continue;
+        }
+        fin = nm_step(S, fc[hit], A.fatol, A.xatol, false);
+        if (fin || S.phase == PH_REFLECT) break;  // search over, or the next iteration starts
       }
     }
-    const int ab = best / R;
-    const double th0 = rf[3 * best + 1], th1 = rf[3 * best + 2];
-    const double kq = (lane < m) ? A.dist[(long long)q * m + lane] : 0.0;
-    double mean = posterior_mean<M>(th0, th1, c_jit10[ab], P, y, kq, m, lane, Lt, A.guard);
-    __syncwarp();
-    if (lane == 0) {
-      A.done[qj] = 0;  // leave the counters clean for the next launch
-      const long long op = (long long)q * A.ld_pred + j;
-      if (A.add) mean = mean + A.add[op];
-      A.pred[op] = mean;
-      if (A.theta_opt) {
-        A.theta_opt[gqj * 2] = th0;
-        A.theta_opt[gqj * 2 + 1] = th1;
-      }
-      if (A.jitter_opt) A.jitter_opt[gqj] = (double)(ab - 20);
-      if (A.fval_opt) A.fval_opt[gqj] = fb;
-    }
+    if (w == 0)
+      finish_search<M>(A, task, S.sx[0][0], S.sx[0][1], fmin(fmin(S.sf[0], S.sf[1]), S.sf[2]), S.fcalls, P, y, lane, Lt);
+    __syncthreads();
   }
 }
 
@@ -1038,8 +1209,9 @@ static inline size_t pad256(size_t b) { return ((b + 255) / 256) * 256; }
 // workspace of a fit: [r2 nq*m*m | res ntasks*3 | done nq*d]
 size_t gp_prep_bytes(int nq, int m) { return sizeof(double) * (size_t)nq * m * m; }
 size_t gp_fit_ws_bytes(int nq, int d, int m, int R) {
-  return pad256(gp_prep_bytes(nq, m)) + pad256(sizeof(double) * 3 * (size_t)nq * d * NNGP_N_JITTER * R) +
-         pad256(sizeof(unsigned int) * (size_t)nq * d);
+  const size_t nt = (size_t)nq * d * NNGP_N_JITTER * R;
+  return pad256(gp_prep_bytes(nq, m)) + pad256(sizeof(double) * 3 * nt) + pad256(sizeof(unsigned int) * (size_t)nq * d) +
+         pad256(sizeof(double) * 12 * nt) + pad256(sizeof(int) * nt);  // + parked simplices and ids of the long searches
 }
 size_t gp_fit_done_offset(int nq, int d, int m, int R) {
   return pad256(gp_prep_bytes(nq, m)) + pad256(sizeof(double) * 3 * (size_t)nq * d * NNGP_N_JITTER * R);
@@ -1083,6 +1255,17 @@ static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
   ProfScope prof(h, 3, st);
   gp_fit_predict_kernel<M><<<(unsigned)blocks, GP_WARPS * 32, smem, st>>>(A);
   h->launches++;
+  if (A.budget > 0) {
+    bool& set2 = h->attr_spec[M / 2];
+    if (!set2) {
+      NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_spec_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set2 = true;
+    }
+    long long blocks2 = (long long)sms * ctas_per_sm;
+    if (blocks2 > A.ntasks) blocks2 = A.ntasks;
+    gp_fit_spec_kernel<M><<<(unsigned)blocks2, GP_WARPS * 32, smem, st>>>(A);
+    h->launches++;
+  }
   NNGP_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1166,16 +1349,28 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.r2 = (const double*)base;
   A.res = (double*)(base + pad256(gp_prep_bytes(nq, m)));
   A.done = (unsigned int*)(base + gp_fit_done_offset(nq, d, m, R));
+  {
+    const size_t nt = (size_t)nq * d * NNGP_N_JITTER * R;
+    char* after = base + gp_fit_done_offset(nq, d, m, R) + pad256(sizeof(unsigned int) * (size_t)nq * d);
+    A.saves = (double*)after;
+    A.cont_list = (int*)(after + pad256(sizeof(double) * 12 * nt));
+  }
   A.queue = queue;
   A.order = order;
   A.pred = d_pred; A.theta_opt = d_theta_opt; A.jitter_opt = d_jitter_opt; A.fval_opt = d_fval_opt;
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
   A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
+  A.budget = 0; A.cont_count = nullptr; A.queue2 = nullptr;
   if (m > NNGP_MAX_NEIGHBOURS) return fit_big_launch(h, A, nq * dl, st);
   int rc = 0;
   const bool grouped = (h->fit_mode == 2) || (h->fit_mode == 0 && nq >= 4 && m <= 20);
   if (!grouped) {
+    if (h->fit_budget >= 3) {
+      A.budget = h->fit_budget;
+      A.cont_count = queue + 1;
+      A.queue2 = queue + 2;
+    }
     DISPATCH_M(m, rc = fit_launch_m<MM>(h, A, st));
   } else {
     const int nqj = nq * dl;

@@ -838,3 +838,40 @@ def test_more_than_32_neighbours(handle, n, d, m):
     assert np.all(out["nfev"] >= 3) and np.all(out["nfev"] <= 400)
     print(f"m={m}: {same}/{total} searches on the oracle's trajectory, {checked}/{d} optima well conditioned")
     assert same >= 0.4 * total
+
+
+@pytest.mark.parametrize("n,d,m", [(64, 6, 20), (500, 8, 20), (300, 5, 11), (300, 4, 31)])
+def test_continuation_kernel_equals_sequential_search_bitwise(handle, n, d, m):
+    """gp_fit_spec_kernel (the four warps of a CTA evaluate reflection / expansion / both contractions -- or, when
+    every vertex is +inf, reflection / inside contraction / both shrunk vertices -- side by side, the state machine
+    consumes them in SciPy's order) continues searches parked after `budget` evaluations: thetas, objective values,
+    evaluation counts, selection and prediction must be the bits of the purely sequential search, whatever the
+    budget (3 = every search is continued from its initial simplex)."""
+    rng = np.random.default_rng(70 + m)
+    if n == 64:   # steady-state-like: identical rows, searches that run to 400 evaluations on +inf
+        x = np.tile(rng.uniform(-1, 1, (1, d)), (n, 1))
+        x[:8] += 1e-3 * rng.standard_normal((8, d))
+        y = 1e-4 * rng.standard_normal((n, d))
+        q = x[20:21] + 0.0
+    else:
+        x, y = make_dataset(rng, n, d)
+        x[5:8] = x[4]
+        y[5:8] = y[4]
+        q = x[4:5] + 1e-4 * rng.standard_normal((1, d))
+    handle.dataset_reset()
+    handle.dataset_reserve(n, d)
+    handle.dataset_append_host(x, y)
+    starts = rng.integers(-8, 0, (1, d, 9, 1, 2)).astype(np.int8)
+    res = {}
+    try:
+        handle.set_fit_mode("warp")
+        for budget in (0, 100, 30, 3):
+            handle.set_fit_budget(budget)
+            res[budget] = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+    finally:
+        handle.set_fit_budget(100)
+        handle.set_fit_mode("auto")
+    for budget in (100, 30, 3):
+        for key in ("nfev", "thetas", "fvals", "theta_opt", "fval_opt", "jitter_opt", "pred"):
+            assert np.array_equal(res[0][key], res[budget][key], equal_nan=True), (key, budget)
+    assert res[0]["nfev"].max() > 100, "the case must contain searches longer than the default budget"
