@@ -154,7 +154,8 @@ double nngp_get_pivot_guard(nngp_handle_t h);
  * search per warp, 2 several searches per warp (32 / (m/2)).  Results are bit-identical; only the speed differs
  * (DESIGN.md section 4.5).  Environment override at nngp_create: NNGP_FIT_MODE=auto|warp|grouped.              */
 int nngp_set_fit_mode(nngp_handle_t h, int mode);
-/* One-search-per-warp kernel only: a search still running after `evaluations` objective evaluations (default 100; 0 = never)
+/* One-search-per-warp kernel only: a search still running after `evaluations` objective evaluations (0 = never, the default:
+ * the continuation did not pay in the measurements of profiles/r02/fit_kernel_variants.log)
  * is continued by a second kernel in which the four warps of a CTA evaluate the candidate points of a Nelder-Mead iteration
  * side by side -- same decisions and bits, half the serial latency of the searches that end a launch.  NNGP_FIT_BUDGET. */
 int nngp_set_fit_budget(nngp_handle_t h, int evaluations);

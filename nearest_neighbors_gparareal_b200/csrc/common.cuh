@@ -69,8 +69,9 @@ struct nngp_handle_s {
   bool attr_mean[17] = {false};
   bool attr_big = false;
   bool attr_spec[17] = {false};
-  // evaluations after which a search is handed to the four-warp continuation kernel (0: never); NNGP_FIT_BUDGET
-  int fit_budget = 100;
+  // evaluations after which a search is handed to the four-warp continuation kernel (0: never, the default: measured
+  // slower than the sequential search at 1 and at 8 GPUs, profiles/r02/fit_kernel_variants.log); NNGP_FIT_BUDGET
+  int fit_budget = 0;
   // which search kernel a fit launches: 0 auto (several searches per warp for batched queries with m <= 20, where it
   // is 1.4-4x faster; one search per warp for the serial sweep, whose searches fail early and cheaply 45 % of the
   // time -- DESIGN.md section 4.5), 1 always one search per warp, 2 always grouped.  NNGP_FIT_MODE=auto|warp|grouped

@@ -731,7 +731,9 @@ __device__ __forceinline__ NMOut nelder_mead(double s0, double s1, double jit10,
     xr1 = __dsub_rn(__dmul_rn(2.0, xb1), sx[2][1]);
     phase = PH_REFLECT; p0 = xr0; p1 = xr1;
     cmask = 0;
-    if (budget > 0 && fcalls >= budget) {  // iteration boundary: sorted simplex, nothing pending
+    // iteration boundary: sorted simplex, nothing pending.  Searches whose vertices are all +inf stay here: their
+    // iterations cost four head checks in four lanes (below), cheaper than a CTA round of the continuation kernel
+    if (budget > 0 && fcalls >= budget && sf[0] != dinf()) {
       unfinished = true;
       break;
     }

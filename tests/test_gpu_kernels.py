@@ -869,7 +869,7 @@ def test_continuation_kernel_equals_sequential_search_bitwise(handle, n, d, m):
             handle.set_fit_budget(budget)
             res[budget] = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
     finally:
-        handle.set_fit_budget(100)
+        handle.set_fit_budget(0)
         handle.set_fit_mode("auto")
     for budget in (100, 30, 3):
         for key in ("nfev", "thetas", "fvals", "theta_opt", "fval_opt", "jitter_opt", "pred"):
