@@ -463,19 +463,19 @@ def main():
     # ---- rooflines of the two kernels that share the step (fine propagator, GP fit): FP64 pipe ------
     peak_src = ("FP64 FMA micro-benchmark run in this process (nngp_bench_fp64: 8 independent DFMA chains per thread, "
                 "148 x 8 CTAs x 256 threads; profiles/r02/fp64_peak.log); MEASURED_PEAKS.json has no FP64 entry; nominal "
-                "B200 FP64 is 37 TFLOP/s (the measured figure is 0.92 of it); the bound is FP64, neither HBM nor tensor "
+                "B200 FP64 is 37 TFLOP/s (the measured figure is 0.914 of it); the bound is FP64, neither HBM nor tensor "
                 "cores: all state is register / shared-memory resident")
     roof_fit = {"kernel": "gp_fit_predict_kernel<20>", "bound": "fp64", "achieved": R["fit_tf"], "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": R["fit_tf"] / fp64_peak if fp64_peak else None, "frac_of_nominal_37": R["fit_tf"] / 37.0,
-                "traffic": 279296, "traffic_source": "profiles/r01/fit_r1_final.summary.csv (dram read+write bytes per launch)",
+                "traffic": 282368, "traffic_source": "profiles/r02/sweep_r2.summary.csv (dram read+write bytes per launch)",
                 "peak_source": peak_src,
                 "per_launch": {"launches": R["fit_n"] // steps, "avg_ms": R["fit_ms"] / max(R["fit_n"], 1),
                                "nll_evals": R["nll_evals"] * steps / max(R["fit_n"], 1), "flops_per_eval": nll_flops(m)},
                 "share_of_step": R["fit_ms"] / (ms_step * steps),
-                "executed_fp64_fraction": None,
+                "executed_fp64_pipe_frac": 0.497, "executed_source": "profiles/r02/sweep_r2.summary.csv (sm__pipe_fp64_cycles_active, steady-state slice)",
                 "note": "algorithmic flops E(m) per objective evaluation; the kernel executes ~8x that in FP64 lane-operations "
-                        "(20 of 32 lanes hold rows, full-row updates, 17-FMA exponentials): FP64 pipe 48 % busy in "
-                        "profiles/r01/fit_r1_steady.summary.csv; 45 % of the evaluations are failing factorisations that "
+                        "(20 of 32 lanes hold rows, full-row updates, 17-FMA exponentials): FP64 pipe 50 % busy in "
+                        "profiles/r02/sweep_r2.summary.csv; 45 % of the evaluations are failing factorisations that "
                         "leave early (profiles/r02/fit_failing_pivots.log)"}
     roof_rk = {"kernel": "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": R["rk_tf"], "peak": fp64_peak,
                "unit": "TFLOP/s", "frac": R["rk_tf"] / fp64_peak if fp64_peak else None, "frac_of_nominal_37": R["rk_tf"] / 37.0,
@@ -489,6 +489,7 @@ def main():
                                       "tasks, 2 CTAs per SM (csrc/rk.cu launch_fhn_tile_s); algorithmic flops count the "
                                       "dense tableau as the reference evaluates it (SURVEY 8d), the kernel executes the 39+5 "
                                       "structural non-zeros: executed FP64 pipe utilisation 59 % (profiles/r01/rk_tile_r1.summary.csv)"},
+               "executed_fp64_pipe_frac": 0.59,
                "share_of_step": R["fine_ms"] / ms_step}
     roofline, other = (roof_rk, roof_fit) if roof_rk["share_of_step"] >= roof_fit["share_of_step"] else (roof_fit, roof_rk)
     wl = workload_config(args)
