@@ -22,6 +22,12 @@ int nngp_fail(nngp_handle_t h, const char* fmt, ...) {
 
 static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
+// every entry point makes the handle's device current first: a process may hold handles on several devices
+#define NNGP_USE_DEVICE(h)                                                                  \
+  do {                                                                                      \
+    if ((h) != nullptr) cudaSetDevice((h)->device);                                         \
+  } while (0)
+
 ProfScope::ProfScope(nngp_handle_t h_, int cls, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
   if (!on) return;
   nngp_handle_s::ProfRec r;
@@ -220,6 +226,7 @@ int nngp_destroy(nngp_handle_t h) {
 const char* nngp_last_error(nngp_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int nngp_synchronize(nngp_handle_t h, void* stream) {
+  NNGP_USE_DEVICE(h);
   NNGP_CUDA(h, cudaStreamSynchronize(as_stream(stream)));
   return 0;
 }
@@ -249,6 +256,7 @@ int nngp_set_fit_budget(nngp_handle_t h, int evaluations) {
 double nngp_get_pivot_guard(nngp_handle_t h) { return h->pivot_guard / 2.220446049250313e-16; }
 
 int nngp_counters(nngp_handle_t h, long long* nm_runs, long long* nll_evals, int reset) {
+  NNGP_USE_DEVICE(h);
   unsigned long long v[8];
   NNGP_CUDA(h, cudaDeviceSynchronize());
   NNGP_CUDA(h, cudaMemcpy(v, h->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
@@ -267,6 +275,7 @@ int nngp_profile_enable(nngp_handle_t h, int on) {
 }
 
 int nngp_profile_read(nngp_handle_t h, double* ms, long long* counts, int reset) {
+  NNGP_USE_DEVICE(h);
   NNGP_CUDA(h, cudaDeviceSynchronize());
   for (auto& r : h->prof_recs) {
     float t = 0.f;
@@ -290,6 +299,7 @@ int nngp_profile_read(nngp_handle_t h, double* ms, long long* counts, int reset)
 // ---- systems ---------------------------------------------------------------------------
 int nngp_system_create(nngp_handle_t h, int system_id, int d, const double* params, int n_params,
                        int normalize, const double* mn, const double* mx, int* sys_out) {
+  NNGP_USE_DEVICE(h);
   if (!sys_out) return nngp_fail(h, "system_create: sys_out is NULL");
   if (system_id < NNGP_SYS_FHN_ODE || system_id > NNGP_SYS_BURGERS)
     return nngp_fail(h, "system_create: unknown system id %d", system_id);
@@ -321,12 +331,14 @@ static int get_sys(nngp_handle_t h, int sys, const SystemDesc** out) {
 }
 
 int nngp_rhs_eval(nngp_handle_t h, int sys, int n, const double* d_u, double* d_out, void* stream) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   return rhs_launch(h, *s, n, d_u, d_out, as_stream(stream));
 }
 
 int nngp_rhs_eval_host(nngp_handle_t h, int sys, int n, const double* u, double* out) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   const size_t bytes = sizeof(double) * (size_t)n * s->d;
@@ -344,6 +356,7 @@ int nngp_rhs_eval_host(nngp_handle_t h, int sys, int n, const double* u, double*
 int nngp_rk_batch(nngp_handle_t h, int sys, int method, int h_mode, long long steps, int n_slices,
                   const double* d_t0, const double* d_t1, const double* d_u0, long long ld_u0,
                   double* d_u1, long long ld_u1, void* stream) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   return rk_launch(h, *s, method, h_mode, steps, n_slices, d_t0, d_t1, d_u0, ld_u0, d_u1, ld_u1,
@@ -353,6 +366,7 @@ int nngp_rk_batch(nngp_handle_t h, int sys, int method, int h_mode, long long st
 int nngp_rk_batch_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps,
                        int n_slices, const double* t0, const double* t1, const double* u0,
                        double* u1) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   if (n_slices <= 0) return 0;
@@ -383,6 +397,7 @@ int nngp_rk_batch_host(nngp_handle_t h, int sys, int method, int h_mode, long lo
 int nngp_rk_full(nngp_handle_t h, int sys, int method, int h_mode, long long steps, int n_slices,
                  const double* d_t0, const double* d_t1, const double* d_u0, long long ld_u0, double* d_traj,
                  void* stream) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   if (n_slices <= 0) return 0;
@@ -396,6 +411,7 @@ int nngp_rk_full(nngp_handle_t h, int sys, int method, int h_mode, long long ste
 
 int nngp_rk_full_host(nngp_handle_t h, int sys, int method, int h_mode, long long steps, double t0, double t1,
                       const double* u0, double* traj) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   if (steps < 1) return nngp_fail(h, "steps must be >= 1 (got %lld)", steps);
@@ -423,6 +439,7 @@ int nngp_get_tableau(int method, int* stages, double* a, double* b, double* c) {
 
 // ---- dataset ---------------------------------------------------------------------------
 int nngp_dataset_reserve(nngp_handle_t h, long long cap_rows, int d) {
+  NNGP_USE_DEVICE(h);
   if (cap_rows < 1 || d < 1) return nngp_fail(h, "dataset_reserve: cap_rows=%lld d=%d", cap_rows, d);
   if (h->ds_x && h->ds_d == d && h->ds_cap >= cap_rows) return 0;
   if (h->ds_x && h->ds_d != d && h->ds_rows > 0)
@@ -463,10 +480,12 @@ int nngp_dataset_dim(nngp_handle_t h) { return h->ds_d; }
 
 int nngp_dataset_append(nngp_handle_t h, const double* d_x, const double* d_y, long long rows,
                         void* stream) {
+  NNGP_USE_DEVICE(h);
   return dataset_append_launch(h, d_x, d_y, rows, as_stream(stream));
 }
 
 int nngp_dataset_append_host(nngp_handle_t h, const double* x, const double* y, long long rows) {
+  NNGP_USE_DEVICE(h);
   if (rows <= 0) return 0;
   if (!h->ds_x) return nngp_fail(h, "dataset not reserved (call nngp_dataset_reserve)");
   if (h->ds_rows + rows > h->ds_cap) {
@@ -488,17 +507,20 @@ int nngp_dataset_append_host(nngp_handle_t h, const double* x, const double* y, 
 
 int nngp_append_iteration(nngp_handle_t h, const double* d_u_cur, const double* d_uF,
                           const double* d_uG_cur, int N, int I, int d, void* stream) {
+  NNGP_USE_DEVICE(h);
   return append_iteration_launch(h, d_u_cur, d_uF, d_uG_cur, N, I, d, as_stream(stream));
 }
 
 int nngp_rowwise_maxabs_diff(nngp_handle_t h, const double* d_a, const double* d_b, int rows,
                              int d, double* d_err, void* stream) {
+  NNGP_USE_DEVICE(h);
   return rowwise_maxabs_launch(h, d_a, d_b, rows, d, d_err, as_stream(stream));
 }
 
 // ---- kNN -------------------------------------------------------------------------------
 int nngp_knn(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows,
              long long* d_idx, double* d_dist, void* stream) {
+  NNGP_USE_DEVICE(h);
   const long long n = (n_rows > 0) ? n_rows : h->ds_rows;
   void* ws = nngp_workspace(h, knn_workspace_bytes(nq, n, m));
   if (!ws) return nngp_fail(h, "knn: out of device memory for %d x %lld distances", nq, n);
@@ -507,6 +529,7 @@ int nngp_knn(nngp_handle_t h, const double* d_q, int nq, int m, long long n_rows
 
 int nngp_knn_host(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
                   long long* idx, double* dist) {
+  NNGP_USE_DEVICE(h);
   if (nq <= 0) return 0;
   const int d = h->ds_d;
   const size_t bq = Carver::pad(sizeof(double) * (size_t)nq * d);
@@ -545,6 +568,7 @@ int nngp_fit_predict(nngp_handle_t h, const double* d_q, const long long* d_idx,
                      const signed char* d_starts, double fatol, double xatol, double* d_pred,
                      double* d_theta_opt, double* d_jitter_opt, double* d_fval_opt, int* d_nfev,
                      double* d_fvals, double* d_thetas, void* stream) {
+  NNGP_USE_DEVICE(h);
   (void)d_q;
   if (n_restarts < 1) return nngp_fail(h, "fit: n_restarts=%d < 1", n_restarts);
   void *kws, *fws;
@@ -561,6 +585,7 @@ int nngp_fit_predict(nngp_handle_t h, const double* d_q, const long long* d_idx,
 
 int nngp_gp_nll(nngp_handle_t h, const long long* d_idx, int nq, int m, int nt,
                 const double* d_theta, const double* d_jitter10, double* d_nll, void* stream) {
+  NNGP_USE_DEVICE(h);
   void *kws, *fws;
   if (int rc = fit_workspace(h, nq, h->ds_rows, m, 1, &kws, &fws)) return rc;
   cudaStream_t st = as_stream(stream);
@@ -571,6 +596,7 @@ int nngp_gp_nll(nngp_handle_t h, const long long* d_idx, int nq, int m, int nt,
 int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, const double* d_dist,
                  int nq, int m, const double* d_theta, const double* d_jitter, double* d_pred,
                  void* stream) {
+  NNGP_USE_DEVICE(h);
   (void)d_q;
   void *kws, *fws;
   if (int rc = fit_workspace(h, nq, h->ds_rows, m, 1, &kws, &fws)) return rc;
@@ -591,6 +617,7 @@ int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, lon
                             int n_restarts, const signed char* starts, double fatol, double xatol, int j0, int dl,
                             double* pred, long long* idx, double* theta_opt, double* jitter_opt,
                             double* fval_opt, int* nfev, double* fvals, double* thetas) {
+  NNGP_USE_DEVICE(h);
   if (nq <= 0) return 0;
   if (!h->ds_x) return nngp_fail(h, "predict: dataset is empty");
   const int d = h->ds_d, R = n_restarts;
@@ -680,6 +707,7 @@ int nngp_sweep(nngp_handle_t h, int sys, int method_g, int h_mode, long long ste
                const double* d_t, int N, int I, int m, int n_restarts,
                const signed char* d_starts, double fatol, double xatol, double* d_u_next,
                double* d_uG_next, int d, void* stream) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   if (d != s->d || d != h->ds_d) return nngp_fail(h, "sweep: d=%d, system d=%d, dataset d=%d", d, s->d, h->ds_d);
@@ -724,6 +752,7 @@ int nngp_sweep_shard(nngp_handle_t h, int sys, int method_g, int h_mode, long lo
                      const double* d_t, int N, int I, int i_first, int i_count, int m, int n_restarts,
                      const signed char* d_starts, double fatol, double xatol, double* d_u_next,
                      double* d_uG_next, int d, int j0, int dl, void* stream) {
+  NNGP_USE_DEVICE(h);
   const SystemDesc* s;
   if (int rc = get_sys(h, sys, &s)) return rc;
   if (d != s->d || d != h->ds_d) return nngp_fail(h, "sweep: d=%d, system d=%d, dataset d=%d", d, s->d, h->ds_d);
@@ -764,6 +793,7 @@ int nngp_sweep_shard(nngp_handle_t h, int sys, int method_g, int h_mode, long lo
 
 int nngp_selftest_math(nngp_handle_t h, const double* d_x, int n, double* d_exp_neg, double* d_rcp,
                        double* d_exp10, void* stream) {
+  NNGP_USE_DEVICE(h);
   return selftest_math_launch(h, d_x, n, d_exp_neg, d_rcp, d_exp10, as_stream(stream));
 }
 
@@ -779,6 +809,7 @@ __global__ void fp64_fma_kernel(double* out, int iters, double a, double b) {
 }
 
 int nngp_bench_fp64(nngp_handle_t h, int iters, double* tflops_out) {
+  NNGP_USE_DEVICE(h);
   const int blocks = 148 * 8, threads = 256;
   double* out = (double*)nngp_workspace(h, sizeof(double) * blocks * threads);
   if (!out) return nngp_fail(h, "bench_fp64: out of memory");
@@ -810,6 +841,7 @@ __global__ void copy_kernel(const double2* __restrict__ src, double2* __restrict
 }
 
 int nngp_bench_copy(nngp_handle_t h, long long bytes, double* gbs_out) {
+  NNGP_USE_DEVICE(h);
   const size_t n = (size_t)bytes / sizeof(double2);
   char* ws = (char*)nngp_workspace(h, 2 * n * sizeof(double2));
   if (!ws) return nngp_fail(h, "bench_copy: out of memory");
