@@ -114,7 +114,9 @@ def test_protocol_errors_match_reference():
     s = nn.CudaSolverRK(ode.get_vector_field(), Ng=4, Nf=8, F='RK4', G='RK1', extra_key_is_swallowed=1)
     p = nn.Parareal(ode, s, tspan=[0, 1], N=4, Ng=4, Nf=8, F='RK4', G='RK1')
     with pytest.raises(Exception, match='Not implemented'):
-        p._make_model('gpjax', pool=None)
+        p._make_model('elm', pool=None)            # parareal.py:94-97: unknown / out-of-scope model names
+    gp = p._make_model('gpjax', pool=None)         # GParareal's full GP (models.py:273-473) is available
+    assert gp.name == 'GP' and gp.fatol == 1e-4 and len(gp.thetas) == 3
     s2 = pickle.loads(pickle.dumps(s))
     assert s2.Nf == 8 and s2.ode.name == 'Lorenz'
 
