@@ -373,6 +373,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   // so slot 0 of lanes 0..9 is the leading 5 x 5 block of the matrix.
   double v[NP];
   v[0] = exp_neg(c * P.r2[0]);
+  bool fail5 = false;
   if (!ALPHA) {
     // Pivots 1..4 decided from the leading block alone, with exactly the operations the factorisation below
     // performs on these entries (same fused multiply-adds in the same order: the decision is only anticipated).
@@ -404,15 +405,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     w4 = b43 * ip3;
     d4 = fma(-w4, b43, d4);
     // a failed pivot makes the later ones meaningless, exactly as in the loop below (ok stays false)
-    const bool fail = !(d1 > pmin) || !(d2 > pmin) || !(d3 > pmin) || !(d4 > pmin);
-    if (__any_sync(FULL, fail)) {
-      GpOut bad;
-      bad.amp = amp;
-      bad.c = c;
-      bad.ok = false;
-      bad.val = dinf();
-      return bad;
-    }
+    fail5 = !(d1 > pmin) || !(d2 > pmin) || !(d3 > pmin) || !(d4 > pmin);
   }
   if constexpr (NP > 1) {
     constexpr int NV = NP - 1;
@@ -436,6 +429,18 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
       exp_neg_vec<G2>(xa, oa);
 #pragma unroll
       for (int t = 0; t < G2; t++) v[G + t + 1] = oa[t];
+    }
+  }
+  // the decision of the block above: its dependency chain (ten shuffles, four reciprocals) runs beside the
+  // polynomial evaluation of the other slots, which are independent of it
+  if (!ALPHA) {
+    if (__any_sync(FULL, fail5)) {
+      GpOut bad;
+      bad.amp = amp;
+      bad.c = c;
+      bad.ok = false;
+      bad.val = dinf();
+      return bad;
     }
   }
 #pragma unroll
