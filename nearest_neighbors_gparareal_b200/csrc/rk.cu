@@ -533,7 +533,7 @@ rk_pde_kernel(SysArgs A, int h_mode, long long steps, const double* __restrict__
 template <int TY, int TB>
 struct TileOcc { static constexpr int value = (TY == 2) ? ((TB <= 64) ? 4 : 1) : ((TB <= 128) ? 2 : 1); };
 
-template <int S, int TY, int TB, bool TRAJ>
+template <int S, int TY, int TB, bool TRAJ, bool SHX>
 __global__ void __launch_bounds__(TB, TileOcc<TY, TB>::value)
 rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long long task0, int n_chunks,
                    const double* __restrict__ t0s, const double* __restrict__ t1s,
@@ -557,6 +557,12 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
   const int odn = ((iy0 + TY == dx) ? 0 : iy0 + TY) * dx + ix0;  // row iy0+TY
   const int xl = (ix0 == 0 ? dx : ix0) - 1, xr = (ix0 + 2 == dx) ? 0 : ix0 + 2;
   const int ol0 = iy0 * dx + xl, or0 = iy0 * dx + xr;
+  // shx: the left / right neighbour columns come from the neighbouring lanes of the same block row by shuffle instead
+  // of shared memory (the threads of a block row are hx consecutive lanes; hx a power of two <= 32).  The column loads
+  // they replace touch only every other 8-byte bank pair and alias across the four block rows of a warp: 16 of the 64
+  // shared-memory wavefronts per warp and stage were bank conflicts (profiles/r01/rk_tile_r1.summary.csv).
+  const int lane = threadIdx.x & 31;
+  const int lsrc = (lane & ~(hx - 1)) | ((lane - 1) & (hx - 1)), rsrc = (lane & ~(hx - 1)) | ((lane + 1) & (hx - 1));
   double u[2][NV], k[2][NV][S];
 #pragma unroll
   for (int c = 0; c < 2; c++) {
@@ -611,18 +617,29 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
             *reinterpret_cast<double2*>(buf + c * npts + o00 + r * dx) = make_double2(w[c][2 * r], w[c][2 * r + 1]);
         }
       }
+      double lf[2][TY], rt[2][TY];
+      if (SHX) {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int r = 0; r < TY; r++) {
+            lf[c][r] = __shfl_sync(0xffffffffu, w[c][2 * r + 1], lsrc);
+            rt[c][r] = __shfl_sync(0xffffffffu, w[c][2 * r], rsrc);
+          }
+      }
       __syncthreads();
       double2 up[2], dn[2];
-      double lf[2][TY], rt[2][TY];
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         const double* b = buf + c * npts;
         up[c] = *reinterpret_cast<const double2*>(b + oup);
         dn[c] = *reinterpret_cast<const double2*>(b + odn);
+        if (!SHX) {
 #pragma unroll
-        for (int r = 0; r < TY; r++) {
-          lf[c][r] = b[ol0 + r * dx];
-          rt[c][r] = b[or0 + r * dx];
+          for (int r = 0; r < TY; r++) {
+            lf[c][r] = b[ol0 + r * dx];
+            rt[c][r] = b[or0 + r * dx];
+          }
         }
       }
       if (i + 1 < S) {
@@ -689,20 +706,21 @@ rk_fhn_tile_kernel(SysArgs A, int h_mode, long long steps, int n_slices, long lo
 // the shared-memory request): every launch is perfectly balanced, a slice's state passes from chunk to chunk
 // through u1, and task (c, s) always falls into a later launch than (c-1, s) because a launch is smaller than
 // the number of slices.  Results are bit-identical to the single launch.
-template <int S, int TY, int TB>
-static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long steps, int n, int sms,
+template <int S, int TY, int TB, bool SHX>
+static int launch_fhn_tile_x(const SysArgs& A, int npts, int h_mode, long long steps, int n, int sms,
                              const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
                              long long ld1, cudaStream_t st) {
   const int threads = ((npts / (2 * TY) + 31) / 32) * 32;
   const size_t smem = 2 * sizeof(double) * 2 * npts;
+
   const int per_launch = 2 * sms;
   const char* force = getenv("NNGP_RK_CHUNKS");  // experiments: 0 = never chunk
   if (A.traj != nullptr) {  // every step stored (run_F_full): one launch
-    rk_fhn_tile_kernel<S, TY, TB, true><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
+    rk_fhn_tile_kernel<S, TY, TB, true, SHX><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
     return 1;
   }
   if (TB > 64 || n <= per_launch || steps < 4096 || (force && force[0] == '0')) {
-    rk_fhn_tile_kernel<S, TY, TB, false><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
+    rk_fhn_tile_kernel<S, TY, TB, false, SHX><<<n, threads, smem, st>>>(A, h_mode, steps, n, 0, 1, t0, t1, u0, ld0, u1, ld1);
     return 1;
   }
   // chunks: the smallest count >= 24 that fills the last launch, else 32
@@ -713,19 +731,32 @@ static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long s
       break;
     }
   const size_t smem2 = 80 * 1024;  // > 1/3 of the SM's shared memory: at most two CTAs per SM
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(rk_fhn_tile_kernel<S, TY, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    attr_set = true;
-  }
+  // per device, so set on every fine step (64 launches follow): a process may hold handles on several GPUs
+  cudaFuncSetAttribute(rk_fhn_tile_kernel<S, TY, TB, false, SHX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   const long long total = (long long)n * chunks;
   int launches = 0;
   for (long long task0 = 0; task0 < total; task0 += per_launch) {
     const int grid = (int)((total - task0 < per_launch) ? total - task0 : per_launch);
-    rk_fhn_tile_kernel<S, TY, TB, false><<<grid, threads, smem2, st>>>(A, h_mode, steps, n, task0, chunks, t0, t1, u0, ld0, u1, ld1);
+    rk_fhn_tile_kernel<S, TY, TB, false, SHX><<<grid, threads, smem2, st>>>(A, h_mode, steps, n, task0, chunks, t0, t1, u0, ld0, u1, ld1);
     launches++;
   }
   return launches;
+}
+
+template <int S, int TY, int TB>
+static int launch_fhn_tile_s(const SysArgs& A, int npts, int h_mode, long long steps, int n, int sms,
+                             const double* t0, const double* t1, const double* u0, long long ld0, double* u1,
+                             long long ld1, cudaStream_t st) {
+  // horizontal neighbours by shuffle when a block row is a power-of-two number of consecutive lanes and every warp is full
+  const int hx_ = (int)A.p[0] >> 1;
+  // Measured (profiles/r02/rk_sweep_shuffle.log): by shuffle a LONE slice (<= 1 per SM, a rank of a 4-8 GPU run) steps 6 %
+  // (2x2 blocks) to 11 % (1x2) faster -- the shuffles leave before the barrier and shorten the per-stage dependency chain --
+  // while with several slices per SM the 16 shuffles per thread and stage cost more shared-pipe cycles than the 8 column
+  // loads they replace (512 slices on one GPU: 627 vs 562 ms).  So: shuffle only when the GPU holds at most one slice per SM.
+  const bool shx = getenv("NNGP_RK_NO_SHFL") == nullptr && hx_ >= 1 && hx_ <= 32 && (hx_ & (hx_ - 1)) == 0 &&
+                   (npts / (2 * TY)) % 32 == 0 && n <= sms;
+  if (shx) return launch_fhn_tile_x<S, TY, TB, true>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
+  return launch_fhn_tile_x<S, TY, TB, false>(A, npts, h_mode, steps, n, sms, t0, t1, u0, ld0, u1, ld1, st);
 }
 
 template <int TY, int TB>
@@ -888,13 +919,18 @@ int rk_launch(nngp_handle_t h, const SystemDesc& s, int method, int h_mode, long
       // (tests, experiments); default 2x2: fastest from 256 slices per GPU up and within 3 % of the 1x2
       // blocks below (a lone slice is bound by the per-stage latency chain, ~270 cycles, in every shape;
       // slice-count sweep in profiles/r01/rk_sweep.log).
-      // Tried and rejected (slower): two slices per 128-thread CTA, left/right neighbours by shuffle.
+      // Tried and rejected (slower): two slices per 128-thread CTA; left/right neighbours by shuffle when an SM holds
+      // several slices (it wins for lone slices, see launch_fhn_tile_s).
       const char* force = getenv("NNGP_RK_TILE");
-      int shape = 2;
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      // at most one slice per SM (a rank of a 4-8 GPU run): 1x2 blocks with the horizontal neighbours by shuffle are the
+      // fastest lone-slice shape (257 ms per published fine step against 278 for 2x2 + shuffle, 290-295 without shuffle)
+      const int hx = dx >> 1;
+      int shape = (n_slices <= sms && hx >= 1 && hx <= 32 && (hx & (hx - 1)) == 0 && (npts / 2) % 32 == 0 &&
+                   getenv("NNGP_RK_NO_SHFL") == nullptr) ? 1 : 2;
       if (force && force[0] >= '0' && force[0] <= '2') shape = (force[0] == '0') ? 0 : ((force[0] == '1') ? 2 : 1);
       if (!A.normalize && (dx & 1) == 0 && dx >= 4 && shape != 0) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         int nl = 1;
         if (shape == 2) {
           if (npts / 4 <= 64)
