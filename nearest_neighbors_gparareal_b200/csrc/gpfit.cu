@@ -374,6 +374,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   double v[NP];
   v[0] = exp_neg(c * P.r2[0]);
   bool fail5 = false;
+  double ipb[4] = {0.0, 0.0, 0.0, 0.0};  // reciprocals of pivots 0..3, reused by the first four steps of the factorisation
   if (!ALPHA) {
     // Pivots 1..4 decided from the leading block alone, with exactly the operations the factorisation below
     // performs on these entries (same fused multiply-adds in the same order: the decision is only anticipated).
@@ -406,6 +407,7 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     d4 = fma(-w4, b43, d4);
     // a failed pivot makes the later ones meaningless, exactly as in the loop below (ok stays false)
     fail5 = !(d1 > pmin) || !(d2 > pmin) || !(d3 > pmin) || !(d4 > pmin);
+    ipb[0] = ip0; ipb[1] = ip1; ipb[2] = ip2; ipb[3] = ip3;
   }
   if constexpr (NP > 1) {
     constexpr int NV = NP - 1;
@@ -511,7 +513,8 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
         return bad;
       }
     }
-    const double ip = rcp_pos(p);
+    // pivots 0..3 are the bits the leading-block check already inverted: take its reciprocals off the critical path
+    const double ip = (!ALPHA && k < 4) ? ipb[k] : rcp_pos(p);
     const double w = a[k] * ip;  // l'_rk
     const double pk = p, zkk = zk;
     if (ALPHA && lane == k) {
