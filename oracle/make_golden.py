@@ -73,6 +73,7 @@ CASES = {
     "hopf_N64_m15_R2": ("hopf", dict(N=64), dict(nn=15, seed=45, n_restarts=2), 5e-7, 37),
     "hopf_N128_m15_R2": ("hopf", dict(N=128), dict(nn=15, seed=45, n_restarts=2), 5e-7, 97),
     "hopf_N256_m15_R2": ("hopf", dict(N=256), dict(nn=15, seed=45, n_restarts=2), 5e-7, 211),
+    "hopf_N512_m15_R2": ("hopf", dict(N=512), dict(nn=15, seed=45, n_restarts=2), 5e-7, 499),
 }
 
 
