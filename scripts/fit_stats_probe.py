@@ -1,3 +1,6 @@
+"""GPU probe: round / packing statistics of the grouped search kernel and first-failing-pivot histogram.
+Needs a statistics build of gpfit.cu (-DNNGP_FIT_STATS, see profiles/r02/fit_failing_pivots.log) loaded through NNGPARA_LIB;
+with the normal build it only prints the search and evaluation counts."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import torch, numpy as np
