@@ -25,7 +25,7 @@ def build(name, driver):
 # lorenz_N32_m11: same K; one conv_int entry moves by one slice (15 vs 16 at iteration 5) with the ulp-level
 # differences of the device objective -- the same sensitivity the reference shows under +-2 ulp noise
 # (oracle/experiments/noise_sensitivity.py).
-# Round 2 fixtures (BASELINE.json configurations at / near their stated sizes): Hopf N=64/128/256 with m=15, R=2,
+# Round 2 fixtures (BASELINE.json configurations at / near their stated sizes): Hopf N=64/128/256/512 with m=15, R=2,
 # FHN-PDE d=128 N=128 m=20, FHN-PDE d=512 N=64 m=20 (the first 64 slices of the target), Burgers d=128 N=128 m=18.
 # Whether K moves by one against the reference run is decided by optimiser trajectories that the reference itself
 # does not reproduce below 1 ulp of its objective; that the device is not BIASED is asserted on 100+ published
@@ -33,7 +33,8 @@ def build(name, driver):
 CASES = {"lorenz_N32_m11": (True, False), "lorenz_N50_m11": (True, False), "lorenz_N50_adaptive": (True, False),
          "hopf_N32_m15": (False, False), "burgers_d32_N32_m12": (False, False), "fhn_d32_N32_m12": (True, True),
          "fhn_d128_N128_m20": (True, True), "hopf_N64_m15_R2": (False, False), "hopf_N128_m15_R2": (False, False),
-         "hopf_N256_m15_R2": (False, False), "burgers_d128_N128_m18": (False, False), "fhn_d512_N64_m20": (False, False)}
+         "hopf_N256_m15_R2": (False, False), "hopf_N512_m15_R2": (False, False),
+         "burgers_d128_N128_m18": (False, False), "fhn_d512_N64_m20": (False, False)}
 CASES = {k: v for k, v in CASES.items() if __import__("os").path.exists(
     __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", f"run_{k}.npz"))}
 

@@ -512,6 +512,9 @@ def test_predict_on_reference_run_samples(handle, name):
             assert abs(out["pred"][0, j] - want) <= tol * abs(want) + 1e-14, (j, out["pred"][0, j], want, cond)
             same_pred += bool(abs(out["pred"][0, j] - s["preds"][j]) <= 1e-8 * abs(s["preds"][j]) + 1e-13)
     assert as_good >= 0.9 * total, (as_good, total)
+    # measured on the B200 (profiles/r02): 24/24 Lorenz, 19/24 Hopf, 27/28 Burgers, 20/21 FHN recorded predictions
+    # reproduced to 1e-8 relative; the rest are selections among equally good searches (previous assert)
+    assert same_pred >= 0.75 * total, (same_pred, total)
     print(f"{name}: optimum as good as the reference's in {as_good}/{total}, identical prediction in {same_pred}/{total}")
 
 
