@@ -151,8 +151,10 @@ int nngp_gp_mean(nngp_handle_t h, const double* d_q, const long long* d_idx, con
 int nngp_set_pivot_guard(nngp_handle_t h, double ulps);
 double nngp_get_pivot_guard(nngp_handle_t h);
 /* Which search kernel nngp_fit_predict / nngp_predict_host / nngp_sweep launch: 0 auto (default), 1 one Nelder-Mead
- * search per warp, 2 several searches per warp (32 / (m/2)).  Results are bit-identical; only the speed differs
- * (DESIGN.md section 4.5).  Environment override at nngp_create: NNGP_FIT_MODE=auto|warp|grouped.              */
+ * search per warp, 2 several searches per warp (32 / (m/2)), 3 four warps per search (the candidate points of an
+ * iteration evaluated side by side: for launches with fewer searches than warp slots, i.e. the dimension-sharded
+ * sweep).  Results are bit-identical; only the speed differs.
+ * Environment override at nngp_create: NNGP_FIT_MODE=auto|warp|grouped|quad.                                    */
 int nngp_set_fit_mode(nngp_handle_t h, int mode);
 /* One-search-per-warp kernel only: a search still running after `evaluations` objective evaluations (0 = never, the default:
  * the continuation did not pay in the measurements of profiles/r02/fit_kernel_variants.log)

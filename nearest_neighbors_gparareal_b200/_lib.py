@@ -306,7 +306,7 @@ class Handle:
 
     def set_fit_mode(self, mode):
         """'auto' | 'warp' (one search per warp) | 'grouped' (several searches per warp); same bits either way"""
-        self.check(self.lib.nngp_set_fit_mode(self.h, {"auto": 0, "warp": 1, "grouped": 2}[mode]))
+        self.check(self.lib.nngp_set_fit_mode(self.h, {"auto": 0, "warp": 1, "grouped": 2, "quad": 3}[mode]))
 
     def set_fit_budget(self, evaluations):
         """evaluations after which a search moves to the four-warp continuation kernel (0: never); same bits"""

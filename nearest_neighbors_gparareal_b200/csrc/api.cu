@@ -155,7 +155,7 @@ int nngp_create(int device, nngp_handle_t* out) {
   nngp_handle_t h = new nngp_handle_s();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  if (const char* fm = getenv("NNGP_FIT_MODE")) h->fit_mode = (strcmp(fm, "warp") == 0) ? 1 : (strcmp(fm, "grouped") == 0) ? 2 : 0;
+  if (const char* fm = getenv("NNGP_FIT_MODE")) h->fit_mode = (strcmp(fm, "warp") == 0) ? 1 : (strcmp(fm, "grouped") == 0) ? 2 : (strcmp(fm, "quad") == 0) ? 3 : 0;
   if (getenv("NNGP_FIT_LEGACY")) h->fit_mode = 1;
   if (const char* b = getenv("NNGP_FIT_BUDGET")) h->fit_budget = atoi(b);
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -242,7 +242,7 @@ int nngp_set_pivot_guard(nngp_handle_t h, double ulps) {
 }
 
 int nngp_set_fit_mode(nngp_handle_t h, int mode) {
-  if (mode < 0 || mode > 2) return nngp_fail(h, "set_fit_mode: mode=%d outside {0 auto, 1 warp, 2 grouped}", mode);
+  if (mode < 0 || mode > 3) return nngp_fail(h, "set_fit_mode: mode=%d outside {0 auto, 1 warp, 2 grouped, 3 quad}", mode);
   h->fit_mode = mode;
   return 0;
 }

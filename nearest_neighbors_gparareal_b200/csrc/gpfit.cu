@@ -33,6 +33,10 @@
 #include <cmath>
 #include <cstdlib>
 
+#ifndef NNGP_PIVOT_AHEAD
+#define NNGP_PIVOT_AHEAD 0  // see gp_core
+#endif
+
 static constexpr int GP_WARPS = 4;  // warps per CTA of the persistent fit kernel
 static constexpr unsigned FULL = 0xffffffffu;
 
@@ -490,7 +494,15 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
   double inv_own = 1.0, w_own = 0.0;  // ALPHA: 1/d_r and (L'^-1 y)_r of the own row
   bool ok = true;
   double u[M];
-  double p = shfl(dd, 0), zk = shfl(z, 0);
+  // NNGP_PIVOT_AHEAD (compile-time variant, off): the next pivot is formed redundantly in every lane from row
+  // k+1's diagonal (pn) and its column-k entry (bn), both broadcast one step ahead, with the very operations row
+  // k+1 applies to itself (bit-identical): the shuffle leaves the reciprocal -> scale -> update chain that
+  // serialises the M steps.  Measured (profiles/r02/fit_kernel_variants.log): slower where the sweep is
+  // throughput-bound (1 GPU, 357 -> 376 ms per iteration).
+  double p = dd0, zk = shfl(z, 0);
+#if NNGP_PIVOT_AHEAD
+  double pn = dd0, bn = (M > 1) ? shfl(a[0], 1) : 0.0;
+#endif
   if (lane > 0 && lane < M) Kt[lane] = a[0];
   __syncwarp();
   load_col(0, u);
@@ -525,7 +537,15 @@ __device__ __forceinline__ GpOut gp_core(double th0, double th1, double jit10, c
     z = fma(-w, zk, z);
     if (k + 1 < M) {
       a[k + 1] = fma(-w, u[k + 1], a[k + 1]);
+#if NNGP_PIVOT_AHEAD
+      p = fma(-(bn * ip), bn, pn);  // == row k+1's dd after this step, bit for bit
+      if (k + 2 < M) {
+        pn = shfl(dd, k + 2);
+        bn = shfl(a[k + 1], k + 2);
+      }
+#else
       p = shfl(dd, k + 1);
+#endif
       zk = shfl(z, k + 1);
       if (k + 2 < M) {
         if (lane > k + 1 && lane < M) Kt[(k + 1) * LD + lane] = a[k + 1];
@@ -808,6 +828,7 @@ struct FitArgs {
   int* cont_list;
   unsigned int* cont_count;
   unsigned int* queue2;
+  int quad_all;           // 1: gp_fit_spec_kernel runs whole searches, four warps each (no first kernel)
 };
 
 template <int M>
@@ -894,6 +915,7 @@ __device__ __forceinline__ void finish_search(const FitArgs& A, int task, double
 #ifndef FIT_OCC20
 #define FIT_OCC20 3
 #endif
+static inline int FitOccRuntime(int m) { return (m <= 12) ? 4 : ((m <= 20) ? FIT_OCC20 : 2); }
 template <int M> struct FitOcc { static constexpr int value = (M <= 12) ? 4 : ((M <= 20) ? FIT_OCC20 : 2); };
 
 template <int M>
@@ -970,13 +992,19 @@ gp_fit_spec_kernel(FitArgs A) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* Lt = sm + w * (M * (M + 2));
   const double hml = (m / 2.0) * 1.8378770664093453;
+  const bool scratch = A.quad_all != 0;  // whole searches (queue / order / starts) instead of parked ones
   PairSlots<M> P;
   pair_slots_init<M>(P, lane, m);
   int q_loaded = -1;
   for (;;) {
     if (threadIdx.x == 0) {
-      const unsigned pos = atomicAdd(A.queue2, 1u);
-      s_task = (pos < *A.cont_count) ? A.cont_list[pos] : -1;
+      if (scratch) {
+        const unsigned pos = atomicAdd(A.queue, 1u);
+        s_task = (pos < (unsigned)A.ntasks) ? (A.order ? A.order[pos] : (int)pos) : -1;
+      } else {
+        const unsigned pos = atomicAdd(A.queue2, 1u);
+        s_task = (pos < *A.cont_count) ? A.cont_list[pos] : -1;
+      }
     }
     __syncthreads();
     const int task = s_task;
@@ -991,8 +1019,11 @@ gp_fit_spec_kernel(FitArgs A) {
     }
     const double y = (lane < m) ? A.Y[A.idx[(long long)q * m + lane] * d + j] : 0.0;
     NMState S;
-    nm_init(S, -1.0, -1.0);
-    {
+    if (scratch) {
+      const signed char* st = A.starts + (((long long)q * d + j) * nruns + run) * 2;
+      nm_init(S, (double)st[0], (double)st[1]);
+    } else {
+      nm_init(S, -1.0, -1.0);
       const double* sv = A.saves + (long long)task * 12;
 #pragma unroll
       for (int v = 0; v < 3; v++) {
@@ -1012,51 +1043,74 @@ gp_fit_spec_kernel(FitArgs A) {
       S.p1 = S.xr1;
     }
     bool fin = false;
-    while (!fin) {
-      double c0[4], c1[4], fc[4];
-      int navail = 4;
-      const double w0 = S.sx[2][0], w1 = S.sx[2][1];
-      c0[0] = S.xr0; c1[0] = S.xr1;
-      if (S.sf[0] == dinf()) {  // every vertex +inf: reflection, inside contraction, the two shrunk vertices
-        c0[1] = __dadd_rn(__dmul_rn(0.5, S.xb0), __dmul_rn(0.5, w0)); c1[1] = __dadd_rn(__dmul_rn(0.5, S.xb1), __dmul_rn(0.5, w1));
-        c0[2] = shrink_to(S.sx[0][0], S.sx[1][0]); c1[2] = shrink_to(S.sx[0][1], S.sx[1][1]);
-        c0[3] = shrink_to(S.sx[0][0], w0); c1[3] = shrink_to(S.sx[0][1], w1);
-      } else {                  // reflection, expansion, outside contraction, inside contraction
-        c0[1] = __dsub_rn(__dmul_rn(3.0, S.xb0), __dmul_rn(2.0, w0)); c1[1] = __dsub_rn(__dmul_rn(3.0, S.xb1), __dmul_rn(2.0, w1));
-        c0[2] = __dsub_rn(__dmul_rn(1.5, S.xb0), __dmul_rn(0.5, w0)); c1[2] = __dsub_rn(__dmul_rn(1.5, S.xb1), __dmul_rn(0.5, w1));
-        c0[3] = __dadd_rn(__dmul_rn(0.5, S.xb0), __dmul_rn(0.5, w0)); c1[3] = __dadd_rn(__dmul_rn(0.5, S.xb1), __dmul_rn(0.5, w1));
-      }
-      {
-        const double f = gp_core<M, false>(c0[w], c1[w], jit10, P, y, m, lane, Lt, hml, A.guard).val;
+    // The previous iteration contracted inside or shrank: the searches that last (a collapsing simplex in the
+    // rounding noise of a singular kernel matrix) do so in long runs, and such an iteration asks for the
+    // reflection, the inside contraction and the two shrunk vertices -- all four known when it starts.
+    bool shrinking = false;
+    auto eval_round = [&](const double (&c0)[4], const double (&c1)[4], int navail, double (&fc)[4]) {
+      const double t0 = (w == 0) ? c0[0] : (w == 1) ? c0[1] : (w == 2) ? c0[2] : c0[3];
+      const double t1 = (w == 0) ? c1[0] : (w == 1) ? c1[1] : (w == 2) ? c1[2] : c1[3];
+      if (w < navail) {
+        const double f = gp_core<M, false>(t0, t1, jit10, P, y, m, lane, Lt, hml, A.guard).val;
         if (lane == 0) s_f[w] = f;
       }
       __syncthreads();
 #pragma unroll
       for (int v = 0; v < 4; v++) fc[v] = s_f[v];
       __syncthreads();
+    };
+    while (!fin) {
+      double c0[4], c1[4], fc[4];
+      int navail = 4;
+      const double w0 = S.sx[2][0], w1 = S.sx[2][1];
+      const double s10 = shrink_to(S.sx[0][0], S.sx[1][0]), s11 = shrink_to(S.sx[0][1], S.sx[1][1]);
+      const double s20 = shrink_to(S.sx[0][0], w0), s21 = shrink_to(S.sx[0][1], w1);
+      if (S.phase == PH_INIT0) {  // the three vertices of the initial simplex
+        c0[0] = S.sx[0][0]; c1[0] = S.sx[0][1];
+        c0[1] = S.sx[1][0]; c1[1] = S.sx[1][1];
+        c0[2] = S.sx[2][0]; c1[2] = S.sx[2][1];
+        c0[3] = c0[0]; c1[3] = c1[0];
+        navail = 3;
+      } else {
+        c0[0] = S.xr0; c1[0] = S.xr1;
+        // inside contraction (1-psi)*xbar + psi*worst
+        const double i0 = __dadd_rn(__dmul_rn(0.5, S.xb0), __dmul_rn(0.5, w0)), i1 = __dadd_rn(__dmul_rn(0.5, S.xb1), __dmul_rn(0.5, w1));
+        if (S.sf[0] == dinf() || shrinking) {  // reflection, inside contraction, the two shrunk vertices
+          c0[1] = i0; c1[1] = i1;
+          c0[2] = s10; c1[2] = s11;
+          c0[3] = s20; c1[3] = s21;
+        } else {                  // reflection, expansion, outside contraction, inside contraction
+          c0[1] = __dsub_rn(__dmul_rn(3.0, S.xb0), __dmul_rn(2.0, w0)); c1[1] = __dsub_rn(__dmul_rn(3.0, S.xb1), __dmul_rn(2.0, w1));
+          c0[2] = __dsub_rn(__dmul_rn(1.5, S.xb0), __dmul_rn(0.5, w0)); c1[2] = __dsub_rn(__dmul_rn(1.5, S.xb1), __dmul_rn(0.5, w1));
+          c0[3] = i0; c1[3] = i1;
+        }
+      }
+      shrinking = false;
+      eval_round(c0, c1, navail, fc);
       for (;;) {  // consume in the order the state machine asks (uniform over the CTA: every warp holds the same state)
         int hit = -1;
 #pragma unroll
         for (int v = 3; v >= 0; v--)
           if (v < navail && S.p0 == c0[v] && S.p1 == c1[v]) hit = v;
         if (hit < 0) {
-          // not among the evaluated points (a shrink after a finite contraction): evaluate it now -- and the second
-          // shrunk vertex with it, which the state machine will ask for next
+          // not among the evaluated points: evaluate it now, together with the points that can follow it in this
+          // iteration (the shrunk vertices after a contraction; s10/s20 still describe them: the simplex only
+          // changes when the iteration ends)
           c0[0] = S.p0; c1[0] = S.p1;
-          const bool two = (S.phase == PH_SHRINK1);
-          c0[1] = two ? shrink_to(S.sx[0][0], S.sx[2][0]) : S.p0;
-          c1[1] = two ? shrink_to(S.sx[0][1], S.sx[2][1]) : S.p1;
-          navail = 2;
-          if (w < 2) {
-            const double f = gp_core<M, false>(c0[w], c1[w], jit10, P, y, m, lane, Lt, hml, A.guard).val;
-            if (lane == 0) s_f[w] = f;
+          navail = 1;
+          if (S.phase == PH_SHRINK1) {
+            c0[1] = s20; c1[1] = s21;
+            navail = 2;
+          } else if (S.phase == PH_OUTC) {
+            c0[1] = s10; c1[1] = s11;
+            c0[2] = s20; c1[2] = s21;
+            navail = 3;
           }
-          __syncthreads();
-          fc[0] = s_f[0];
-          fc[1] = s_f[1];
-          __syncthreads();
+          for (int v = navail; v < 4; v++) { c0[v] = c0[0]; c1[v] = c1[0]; }
+          eval_round(c0, c1, navail, fc);
           continue;
         }
+        if (S.phase == PH_INC || S.phase == PH_SHRINK1 || S.phase == PH_SHRINK2) shrinking = true;
         fin = nm_step(S, fc[hit], A.fatol, A.xatol, false);
         if (fin || S.phase == PH_REFLECT) break;  // search over, or the next iteration starts
       }
@@ -1263,6 +1317,19 @@ static int fit_launch_m(nngp_handle_t h, const FitArgs& A, cudaStream_t st) {
   const long long need = (A.ntasks + GP_WARPS - 1) / GP_WARPS;
   if (blocks > need) blocks = need;
   ProfScope prof(h, 3, st);
+  if (A.quad_all) {
+    bool& set2 = h->attr_spec[M / 2];
+    if (!set2) {
+      NNGP_CUDA(h, cudaFuncSetAttribute(gp_fit_spec_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set2 = true;
+    }
+    long long blocks2 = (long long)sms * ctas_per_sm;
+    if (blocks2 > A.ntasks) blocks2 = A.ntasks;
+    gp_fit_spec_kernel<M><<<(unsigned)blocks2, GP_WARPS * 32, smem, st>>>(A);
+    h->launches++;
+    NNGP_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   gp_fit_predict_kernel<M><<<(unsigned)blocks, GP_WARPS * 32, smem, st>>>(A);
   h->launches++;
   if (A.budget > 0) {
@@ -1371,12 +1438,18 @@ int gp_fit_predict_launch(nngp_handle_t h, const long long* d_idx, const double*
   A.nfev = d_nfev; A.fvals = d_fvals; A.thetas = d_thetas; A.counters = h->d_counters;
   A.d = d; A.m = m; A.R = R; A.ntasks = (int)ntasks; A.j0 = j0; A.dl = dl;
   A.head_batch = (getenv("NNGP_FIT_NO_HEAD_BATCH") == nullptr) ? 1 : 0; A.ld_pred = ld_pred; A.fatol = fatol; A.xatol = xatol; A.guard = h->pivot_guard;
-  A.budget = 0; A.cont_count = nullptr; A.queue2 = nullptr;
+  A.budget = 0; A.cont_count = nullptr; A.queue2 = nullptr; A.quad_all = 0;
   if (m > NNGP_MAX_NEIGHBOURS) return fit_big_launch(h, A, nq * dl, st);
   int rc = 0;
   const bool grouped = (h->fit_mode == 2) || (h->fit_mode == 0 && nq >= 4 && m <= 20);
   if (!grouped) {
-    if (h->fit_budget >= 3) {
+    // Few searches per launch (a rank's share of the dimension-sharded sweep): the launch lasts as long as its
+    // longest search, most warp slots idle -> four warps per search.  Measured per predict at the FHN target
+    // (profiles/r02/fit_kernel_variants.log): 576 searches 388 -> 266 us, 1152: 429 -> 375 us, 2304: 504 -> 654 us.
+    const long long quad_limit = 3LL * h->sm_count * FitOccRuntime(m);
+    if (h->fit_mode == 3 || (h->fit_mode == 0 && ntasks <= quad_limit)) {
+      A.quad_all = 1;
+    } else if (h->fit_budget >= 3) {
       A.budget = h->fit_budget;
       A.cont_count = queue + 1;
       A.queue2 = queue + 2;

@@ -871,10 +871,13 @@ def test_continuation_kernel_equals_sequential_search_bitwise(handle, n, d, m):
         for budget in (0, 100, 30, 3):
             handle.set_fit_budget(budget)
             res[budget] = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
+        handle.set_fit_budget(0)
+        handle.set_fit_mode("quad")   # whole searches on four warps, from the initial simplex
+        res["quad"] = handle.predict_host(q, m, starts, 1, 0.1, 0.1, details=True)
     finally:
         handle.set_fit_budget(0)
         handle.set_fit_mode("auto")
-    for budget in (100, 30, 3):
+    for budget in (100, 30, 3, "quad"):
         for key in ("nfev", "thetas", "fvals", "theta_opt", "fval_opt", "jitter_opt", "pred"):
             assert np.array_equal(res[0][key], res[budget][key], equal_nan=True), (key, budget)
     assert res[0]["nfev"].max() > 100, "the case must contain searches longer than the default budget"
