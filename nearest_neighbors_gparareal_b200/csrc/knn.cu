@@ -509,6 +509,174 @@ scan_select_kernel(const double* __restrict__ XT, const double* __restrict__ X, 
   }
 }
 
+// Small datasets (the sweep: 512 .. ~3000 rows): scan_select_kernel above has one thread walk one row with a fixed
+// number of loads in flight, so a 512-row scan is two CTAs waiting 32 times for L2 (52 us per slice, 26 ms per iteration
+// of the FHN target -- profiles/r02/launches_step_r2.summary.csv).  Here a CTA takes 32 rows: all its threads stream
+// the row-major rows (coalesced, 16 independent loads per thread), leave (q_j - x_ij)^2 in a padded shared-memory tile,
+// and 32 threads add their row up in ascending j -- the same operations in the same order, so the same bits.  Level 1
+// is a 32-key bitonic sort in warp 0; level 2 and the neighbour matrix run in the CTA that takes the last ticket; the
+// neighbour rows are staged in the same tile, a column tile at a time.
+static constexpr int TILE_ROWS = 32;
+static constexpr int TILE_COLS = 256;
+static constexpr int TILE_LD = TILE_COLS + 1;
+static constexpr long long KNN_TILE_MAX_ROWS = 24576;  // beyond: more CTAs than two waves, the streaming kernel wins
+
+__global__ void __launch_bounds__(PRO_THREADS)
+scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const double* __restrict__ Q, int m,
+                        double* __restrict__ cand_d, long long* __restrict__ cand_i, unsigned int* tickets,
+                        long long* __restrict__ idx_out, double* __restrict__ dist_out, double* __restrict__ r2) {
+  extern __shared__ double dyn[];  // [d] query | [TILE_ROWS][TILE_LD] tile
+  double* qs = dyn;
+  double* tile = dyn + ((d + 1) & ~1);
+  constexpr int NW = PRO_THREADS / 32;
+  __shared__ double cd[NW * 32];
+  __shared__ long long ci[NW * 32];
+  __shared__ bool last;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const long long IMAX = 0x7fffffffffffffffLL;
+  const int qi = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double* q = Q + (long long)qi * d;
+  for (int e = tid; e < d; e += PRO_THREADS) qs[e] = q[e];
+  const long long lo = (long long)blockIdx.x * TILE_ROWS;
+  const int rows = (int)min((long long)TILE_ROWS, n - lo);
+  const double* xb = X + lo * d;
+  double acc = 0.0;
+  __syncthreads();
+  // warp w streams rows w, w + 8, w + 16, w + 24 of the chunk, its lanes the columns lane + 32 k: 256-byte
+  // coalesced loads, all 32 of a thread independent; the loads of the next column tile are in flight while
+  // the rows of the current one are added up
+  static_assert(TILE_ROWS == 4 * NW && TILE_COLS == 8 * 32, "row / column mapping of the tile");
+  double xv[4][8];
+  auto load_tile = [&](int j0) {
+    const int jn = min(TILE_COLS, d - j0);
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+      const int r = wid + rr * NW;
+      const double* xr = xb + (long long)r * d + j0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = lane + 32 * k;
+        xv[rr][k] = (r < rows && c < jn) ? __ldg(xr + c) : 0.0;
+      }
+    }
+  };
+  load_tile(0);
+  for (int j0 = 0; j0 < d; j0 += TILE_COLS) {
+    const int jn = min(TILE_COLS, d - j0);
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+      const int r = wid + rr * NW;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = lane + 32 * k;
+        if (c < jn) {
+          const double diff = qs[j0 + c] - xv[rr][k];
+          tile[r * TILE_LD + c] = diff * diff;
+        }
+      }
+    }
+    __syncthreads();
+    if (j0 + TILE_COLS < d) load_tile(j0 + TILE_COLS);
+    if (tid < rows) {
+      const double* tr = tile + tid * TILE_LD;
+#pragma unroll 8
+      for (int c = 0; c < jn; c++) acc = acc + tr[c];
+    }
+    __syncthreads();
+  }
+  // level 1: the CTA's rows sorted by (distance, index); the first m are its candidates
+  if (tid < 32) {
+    double kd = (lane < rows) ? acc : INF;
+    long long ki = (lane < rows) ? lo + lane : IMAX;
+    warp_sort32(kd, ki, lane);
+    if (lane < m) {
+      const long long cbase = ((long long)qi * gridDim.x + blockIdx.x) * m;
+      cand_i[cbase + lane] = ki;
+      cand_d[cbase + lane] = (ki == IMAX) ? INF : kd;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(tickets + qi, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // level 2: merge the candidates of all CTAs of this query
+  const long long nc = (long long)gridDim.x * m;
+  long long* io = idx_out + (long long)qi * m;
+  select_topm_cta<NW>(cand_d + (long long)qi * nc, cand_i + (long long)qi * nc, 0, nc, m, io, dist_out + (long long)qi * m,
+                      cd, ci);
+  if (tid == 0) tickets[qi] = 0;  // ready for the next launch
+  if (r2 == nullptr) return;
+  __syncthreads();  // idx_out written by warp 0 of this CTA
+  double* r2q = r2 + (long long)qi * m * m;
+  const int npairs = m * (m + 1) / 2;
+  constexpr int PP = (NNGP_MAX_NEIGHBOURS * (NNGP_MAX_NEIGHBOURS + 1) / 2 + PRO_THREADS - 1) / PRO_THREADS;
+  int pa[PP], pb[PP];
+  double acc2[PP];
+#pragma unroll
+  for (int u = 0; u < PP; u++) {
+    const int pidx = tid + u * PRO_THREADS;
+    int a = 0, b = 0;
+    if (pidx < npairs) {
+      a = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= pidx) a++;
+      while (a * (a + 1) / 2 > pidx) a--;
+      b = pidx - a * (a + 1) / 2;
+    }
+    pa[u] = a;
+    pb[u] = b;
+    acc2[u] = 0.0;
+  }
+  for (int j0 = 0; j0 < d; j0 += TILE_COLS) {
+    const int jn = min(TILE_COLS, d - j0);
+    __syncthreads();
+    {
+      double xv[4][8];
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const int r = wid + rr * NW;
+        const double* xr = X + ((r < m) ? __ldcg(io + r) : 0) * d + j0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int c = lane + 32 * k;
+          xv[rr][k] = (r < m && c < jn) ? __ldg(xr + c) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const int r = wid + rr * NW;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int c = lane + 32 * k;
+          if (r < m && c < jn) tile[r * TILE_LD + c] = xv[rr][k];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PP; u++) {
+      if (tid + u * PRO_THREADS < npairs) {
+        const double *ta = tile + pa[u] * TILE_LD, *tb = tile + pb[u] * TILE_LD;
+        double sacc = acc2[u];
+#pragma unroll 4
+        for (int c = 0; c < jn; c++) {
+          const double diff = ta[c] - tb[c];
+          sacc = sacc + diff * diff;
+        }
+        acc2[u] = sacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PP; u++) {
+    if (tid + u * PRO_THREADS < npairs) {
+      r2q[pa[u] * m + pb[u]] = acc2[u];
+      r2q[pb[u] * m + pa[u]] = acc2[u];
+    }
+  }
+}
+
 // m > 32 (rare: nn='adaptive' past iteration 30): m passes of "smallest key above the last one" by one CTA per query
 __global__ void __launch_bounds__(256)
 select_big_kernel(const double* __restrict__ dist, long long n, int m, long long* __restrict__ idx_out,
@@ -572,7 +740,7 @@ static constexpr int KNN_FUSED_MAX_Q = 4;  // queries per call served by scan_se
 size_t knn_workspace_bytes(int nq, long long n, int m) {
   const long long cr = knn_chunk_rows(nq, n);
   size_t chunks = (size_t)((n + cr - 1) / cr);
-  if (nq <= KNN_FUSED_MAX_Q) chunks = (size_t)((n + PRO_THREADS - 1) / PRO_THREADS);
+  if (nq <= KNN_FUSED_MAX_Q) chunks = (size_t)((n + 31) / 32);  // TILE_ROWS of the small-dataset kernel (>= the 256-row chunks)
   size_t b = knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
   if (chunks > 1 || nq <= KNN_FUSED_MAX_Q) b += 2 * knn_pad256(sizeof(double) * (size_t)nq * chunks * (size_t)m);
   return b;
@@ -582,9 +750,25 @@ size_t knn_workspace_bytes(int nq, long long n, int m) {
 static int scan_select_launch(nngp_handle_t h, const double* d_q, int nq, int m, long long n, long long* d_idx,
                               double* d_dist, double* d_r2, void* ws, cudaStream_t st) {
   const int d = h->ds_d;
-  const unsigned chunks = (unsigned)((n + PRO_THREADS - 1) / PRO_THREADS);
   double* dist = (double*)ws;
   char* base = (char*)ws + knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
+  static const bool no_tile = getenv("NNGP_KNN_NO_TILE") != nullptr;
+  const size_t tile_smem = sizeof(double) * ((size_t)((d + 1) & ~1) + (size_t)TILE_ROWS * TILE_LD);
+  if (n <= KNN_TILE_MAX_ROWS && !no_tile && tile_smem <= 200 * 1024) {
+    const unsigned tchunks = (unsigned)((n + TILE_ROWS - 1) / TILE_ROWS);
+    double* tcand_d = (double*)base;
+    long long* tcand_i = (long long*)(base + knn_pad256(sizeof(double) * (size_t)nq * tchunks * m));
+    if (!h->attr_knn_tile) {
+      NNGP_CUDA(h, cudaFuncSetAttribute(scan_select_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      h->attr_knn_tile = true;
+    }
+    scan_select_tile_kernel<<<dim3(tchunks, nq), PRO_THREADS, tile_smem, st>>>(
+        h->ds_x, n, d, d_q, m, tcand_d, tcand_i, h->d_ticket, d_idx, d_dist, d_r2);
+    h->launches++;
+    NNGP_CUDA(h, cudaGetLastError());
+    return 0;
+  }
+  const unsigned chunks = (unsigned)((n + PRO_THREADS - 1) / PRO_THREADS);
   double* cand_d = (double*)base;
   long long* cand_i = (long long*)(base + knn_pad256(sizeof(double) * (size_t)nq * chunks * m));
   scan_select_kernel<16><<<dim3(chunks, nq), PRO_THREADS, (size_t)d * sizeof(double), st>>>(
