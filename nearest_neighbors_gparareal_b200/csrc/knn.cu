@@ -512,14 +512,102 @@ scan_select_kernel(const double* __restrict__ XT, const double* __restrict__ X, 
 // Small datasets (the sweep: 512 .. ~3000 rows): scan_select_kernel above has one thread walk one row with a fixed
 // number of loads in flight, so a 512-row scan is two CTAs waiting 32 times for L2 (52 us per slice, 26 ms per iteration
 // of the FHN target -- profiles/r02/launches_step_r2.summary.csv).  Here a CTA takes 32 rows: all its threads stream
-// the row-major rows (coalesced, 16 independent loads per thread), leave (q_j - x_ij)^2 in a padded shared-memory tile,
-// and 32 threads add their row up in ascending j -- the same operations in the same order, so the same bits.  Level 1
-// is a 32-key bitonic sort in warp 0; level 2 and the neighbour matrix run in the CTA that takes the last ticket; the
-// neighbour rows are staged in the same tile, a column tile at a time.
-static constexpr int TILE_ROWS = 32;
+// the row-major rows (coalesced), leave (q_j - x_ij)^2 in a padded shared-memory tile, and 32 threads add their row up
+// in ascending j -- the same operations in the same order, so the same bits.  Level 1 is a 32-key bitonic sort in
+// warp 0; level 2 and the neighbour matrix run in the CTA that takes the last ticket, the neighbour rows staged in
+// the same tile, a column tile at a time.
+// The kernel runs once per slice between two launches of the (large) fit kernel, so it starts with a cold instruction
+// cache and executes most of its code once: in-kernel clock stamps showed 3-5x the cycles its arithmetic and memory
+// latencies account for, proportional to the code size of each phase (a fully unrolled version of this kernel:
+// 4 500 instructions, 60 k cycles for the last CTA).  Hence the loops below are deliberately NOT unrolled beyond what
+// keeps enough loads in flight.
+static constexpr int TILE_ROWS = 32;   // rows of the shared tile (the neighbour rows of the r2 phase: m <= 32)
+static constexpr int SCAN_ROWS = 16;   // dataset rows scanned per CTA: with n >= 16 m there are at least m candidate
+                                       // lists and level 2 is bounded by the m-th head (n = 512, m = 20: 32 lists)
 static constexpr int TILE_COLS = 256;
 static constexpr int TILE_LD = TILE_COLS + 1;
-static constexpr long long KNN_TILE_MAX_ROWS = 24576;  // beyond: more CTAs than two waves, the streaming kernel wins
+static constexpr long long KNN_TILE_MAX_ROWS = 8192;   // beyond: the head ranking of level 2 (lists^2 / 256 per thread) outgrows the scan; the streaming kernel takes over
+
+#ifdef NNGP_KNN_TIMING
+__device__ long long g_knn_stamps[16];
+#define KNN_STAMP(k) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || (k) >= 4)) g_knn_stamps[k] = clock64(); } while (0)
+#else
+#define KNN_STAMP(k) do {} while (0)
+#endif
+
+// The total order (isnan, distance, index) with padding last, as a pair of integers compared lexicographically:
+// comparisons become predicate logic (the floating-point version compiles to divergent branches -- 40 k cycles for
+// the level-2 ranks of 320 candidates, measured with in-kernel clock stamps).
+typedef unsigned long long u64;
+static constexpr u64 UKEY_NAN = 0xfffffffffffffffeULL, UKEY_PAD = 0xffffffffffffffffULL;
+__device__ __forceinline__ u64 ukey_of(double d) {
+  if (d != d) return UKEY_NAN;
+  const u64 b = (u64)__double_as_longlong(d + 0.0);  // -0 -> +0: equal distances tie on the index
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double ukey_to_double(u64 k) {
+  if (k >= UKEY_NAN) return (k == UKEY_NAN) ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double(0x7ff0000000000000LL);
+  const u64 b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ bool ukey_less(u64 k1, long long i1, u64 k2, long long i2) {
+  return (k1 < k2) | ((k1 == k2) & (i1 < i2));
+}
+
+// bitonic sort of one key per lane, ascending over the lanes; the network as two rolled loops (see above)
+__device__ __forceinline__ void warp_sort32_compact(u64& k, long long& i, int lane) {
+#pragma unroll 1
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll 1
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const u64 ok = __shfl_xor_sync(0xffffffffu, k, j);
+      const long long oi = __shfl_xor_sync(0xffffffffu, i, j);
+      const bool take_min = ((lane & kk) == 0) == ((lane & j) == 0);
+      const bool less = ukey_less(ok, oi, k, i);
+      const bool take = (take_min == less);
+      k = take ? ok : k;
+      i = take ? oi : i;
+    }
+  }
+}
+
+// rows r = wid, wid + 8, ... (< nrows) of a column tile [j0, j0 + jn) into the shared tile: warp per row, lanes over
+// the columns lane + 32 k (256-byte coalesced loads, 16 of a thread in flight).  SQ: store (q_j - x)^2, else x.
+template <bool SQ, int RG>
+__device__ __forceinline__ void stage_rows(const double* __restrict__ X, const long long* __restrict__ rowid,
+                                           long long row0, int nrows, int d, int j0, int jn,
+                                           const double* __restrict__ qs, double* __restrict__ tile, int wid, int lane) {
+  constexpr int NW = PRO_THREADS / 32;
+  // RG row groups per warp: all their loads (8 RG per thread) in flight at once
+  double xv[RG][8];
+#pragma unroll
+  for (int h = 0; h < RG; h++) {
+    const int r = wid + h * NW;
+    const long long row = (r < nrows) ? (rowid ? __ldcg(rowid + r) : row0 + r) : 0;
+    const double* xr = X + row * d + j0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = lane + 32 * k;
+      xv[h][k] = (r < nrows && c < jn) ? __ldg(xr + c) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < RG; h++) {
+    const int r = wid + h * NW;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = lane + 32 * k;
+      if (c < jn) {
+        if (SQ) {
+          const double diff = qs[j0 + c] - xv[h][k];
+          tile[r * TILE_LD + c] = diff * diff;
+        } else {
+          tile[r * TILE_LD + c] = xv[h][k];
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(PRO_THREADS)
 scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const double* __restrict__ Q, int m,
@@ -529,86 +617,150 @@ scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const 
   double* qs = dyn;
   double* tile = dyn + ((d + 1) & ~1);
   constexpr int NW = PRO_THREADS / 32;
-  __shared__ double cd[NW * 32];
-  __shared__ long long ci[NW * 32];
+  static_assert(TILE_ROWS % NW == 0 && SCAN_ROWS % NW == 0 && SCAN_ROWS <= 32 && TILE_COLS == 8 * 32, "row / column mapping of the tile");
   __shared__ bool last;
+  __shared__ int active[NNGP_MAX_NEIGHBOURS];
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const long long IMAX = 0x7fffffffffffffffLL;
   const int qi = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double* q = Q + (long long)qi * d;
+#pragma unroll 1
   for (int e = tid; e < d; e += PRO_THREADS) qs[e] = q[e];
-  const long long lo = (long long)blockIdx.x * TILE_ROWS;
-  const int rows = (int)min((long long)TILE_ROWS, n - lo);
-  const double* xb = X + lo * d;
+  const long long lo = (long long)blockIdx.x * SCAN_ROWS;
+  const int rows = (int)min((long long)SCAN_ROWS, n - lo);
   double acc = 0.0;
+  KNN_STAMP(0);
   __syncthreads();
-  // warp w streams rows w, w + 8, w + 16, w + 24 of the chunk, its lanes the columns lane + 32 k: 256-byte
-  // coalesced loads, all 32 of a thread independent; the loads of the next column tile are in flight while
-  // the rows of the current one are added up
-  static_assert(TILE_ROWS == 4 * NW && TILE_COLS == 8 * 32, "row / column mapping of the tile");
-  double xv[4][8];
-  auto load_tile = [&](int j0) {
-    const int jn = min(TILE_COLS, d - j0);
-#pragma unroll
-    for (int rr = 0; rr < 4; rr++) {
-      const int r = wid + rr * NW;
-      const double* xr = xb + (long long)r * d + j0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int c = lane + 32 * k;
-        xv[rr][k] = (r < rows && c < jn) ? __ldg(xr + c) : 0.0;
-      }
-    }
-  };
-  load_tile(0);
+#pragma unroll 1
   for (int j0 = 0; j0 < d; j0 += TILE_COLS) {
     const int jn = min(TILE_COLS, d - j0);
-#pragma unroll
-    for (int rr = 0; rr < 4; rr++) {
-      const int r = wid + rr * NW;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int c = lane + 32 * k;
-        if (c < jn) {
-          const double diff = qs[j0 + c] - xv[rr][k];
-          tile[r * TILE_LD + c] = diff * diff;
-        }
-      }
-    }
+    stage_rows<true, SCAN_ROWS / NW>(X, nullptr, lo, rows, d, j0, jn, qs, tile, wid, lane);
     __syncthreads();
-    if (j0 + TILE_COLS < d) load_tile(j0 + TILE_COLS);
     if (tid < rows) {
       const double* tr = tile + tid * TILE_LD;
-#pragma unroll 8
+#pragma unroll 32
       for (int c = 0; c < jn; c++) acc = acc + tr[c];
     }
     __syncthreads();
   }
+  KNN_STAMP(1);
   // level 1: the CTA's rows sorted by (distance, index); the first m are its candidates
   if (tid < 32) {
-    double kd = (lane < rows) ? acc : INF;
+    u64 kk = (lane < rows) ? ukey_of(acc) : UKEY_PAD;
     long long ki = (lane < rows) ? lo + lane : IMAX;
-    warp_sort32(kd, ki, lane);
+    warp_sort32_compact(kk, ki, lane);
     if (lane < m) {
       const long long cbase = ((long long)qi * gridDim.x + blockIdx.x) * m;
       cand_i[cbase + lane] = ki;
-      cand_d[cbase + lane] = (ki == IMAX) ? INF : kd;
+      reinterpret_cast<u64*>(cand_d)[cbase + lane] = kk;  // the integer key; level 2 converts back
     }
   }
+  KNN_STAMP(2);
   __threadfence();
   __syncthreads();
   if (tid == 0) last = (atomicAdd(tickets + qi, 1u) == gridDim.x - 1);
   __syncthreads();
+  KNN_STAMP(3);
   if (!last) return;
   __threadfence();
-  // level 2: merge the candidates of all CTAs of this query
-  const long long nc = (long long)gridDim.x * m;
+  KNN_STAMP(4);
+  // level 2: the m smallest keys of the gridDim.x sorted candidate lists.  With at least m lists, T = the m-th smallest
+  // list head bounds the answer (m heads are <= T), every key <= T sits in one of the m lists whose heads are <= T
+  // ("active"), and the rank of such a key among the active lists is its rank among all candidates: each surviving
+  // key finds its output position by binary searches -- no sorting network, cost independent of the number of lists.
+  // With fewer than m lists all of them are active and nothing is bounded.
+  const int nl = gridDim.x;
   long long* io = idx_out + (long long)qi * m;
-  select_topm_cta<NW>(cand_d + (long long)qi * nc, cand_i + (long long)qi * nc, 0, nc, m, io, dist_out + (long long)qi * m,
-                      cd, ci);
+  {
+    const u64* cdq = reinterpret_cast<const u64*>(cand_d) + (long long)qi * nl * m;
+    const long long* ciq = cand_i + (long long)qi * nl * m;
+    u64* hd = reinterpret_cast<u64*>(tile);                 // [nl] heads
+    long long* hi = reinterpret_cast<long long*>(tile + nl);
+    u64* ad = reinterpret_cast<u64*>(tile + 2 * nl);        // [na][m] active lists
+    long long* ai = reinterpret_cast<long long*>(tile + 2 * nl + NNGP_MAX_NEIGHBOURS * NNGP_MAX_NEIGHBOURS);
+#pragma unroll 1
+    for (int l = tid; l < nl; l += PRO_THREADS) {
+      hd[l] = __ldcg(cdq + (long long)l * m);
+      hi[l] = __ldcg(ciq + (long long)l * m);
+    }
+    __syncthreads();
+    KNN_STAMP(8);
+    const int na = min(nl, m);
+#pragma unroll 1
+    for (int l = tid; l < nl; l += PRO_THREADS) {
+      const u64 kk = hd[l];
+      const long long ki = hi[l];
+      int r = 0;
+#pragma unroll 4
+      for (int t = 0; t < nl; t++) r += ukey_less(hd[t], hi[t], kk, ki) ? 1 : 0;
+      if (r < na) active[r] = l;
+    }
+    __syncthreads();
+    KNN_STAMP(9);
+#pragma unroll 1
+    for (int e = tid; e < na * m; e += PRO_THREADS) {
+      const int a = e / m, pp = e - a * m;
+      ad[e] = __ldcg(cdq + (long long)active[a] * m + pp);
+      ai[e] = __ldcg(ciq + (long long)active[a] * m + pp);
+    }
+    __syncthreads();
+    KNN_STAMP(10);
+    const bool bounded = nl >= m;
+    const u64 tk = ad[(na - 1) * m];
+    const long long ti = ai[(na - 1) * m];
+    // surviving keys (not padding, not above the bound) are packed, then one thread per (survivor, active list) counts
+    // the list's keys below the survivor's (lower bound in a sorted list of m <= 32 entries) and adds it to the rank
+    int* surv = reinterpret_cast<int*>(tile + 2 * nl + 2 * NNGP_MAX_NEIGHBOURS * NNGP_MAX_NEIGHBOURS);
+    int* rankacc = surv + NNGP_MAX_NEIGHBOURS * NNGP_MAX_NEIGHBOURS;
+    __shared__ int n_surv;
+    if (tid == 0) n_surv = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int e = tid; e < na * m; e += PRO_THREADS) {
+      const u64 kk = ad[e];
+      const long long ki = ai[e];
+      if (ki == IMAX || (bounded && ukey_less(tk, ti, kk, ki))) continue;
+      const int pos = atomicAdd(&n_surv, 1);
+      surv[pos] = e;
+      rankacc[pos] = 0;
+    }
+    __syncthreads();
+    const int ns = n_surv;
+#pragma unroll 1
+    for (int t = tid; t < ns * na; t += PRO_THREADS) {
+      const int sidx = t / na, a = t - sidx * na;
+      const int e = surv[sidx];
+      const u64 kk = ad[e];
+      const long long ki = ai[e];
+      int base = 0, len = m;
+#pragma unroll 1
+      for (int step = 0; step < 6; step++) {
+        const int half = len >> 1;
+        const int at = a * m + min(base + half, m - 1);
+        const bool below = (len > 0) & ukey_less(ad[at], ai[at], kk, ki);
+        base = below ? base + half + 1 : base;
+        len = below ? len - half - 1 : half;
+      }
+      if (base) atomicAdd(&rankacc[sidx], base);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sidx = tid; sidx < ns; sidx += PRO_THREADS) {
+      const int rank = rankacc[sidx];
+      if (rank < m) {
+        const int e = surv[sidx];
+        io[rank] = ai[e];
+        dist_out[(long long)qi * m + rank] = ukey_to_double(ad[e]);
+      }
+    }
+  }
+  KNN_STAMP(11);
   if (tid == 0) tickets[qi] = 0;  // ready for the next launch
   if (r2 == nullptr) return;
-  __syncthreads();  // idx_out written by warp 0 of this CTA
+  __threadfence_block();
+  __syncthreads();  // idx_out written by this CTA
+  KNN_STAMP(5);
+  // neighbour matrix: pair (a, b), a >= b, per thread (m (m + 1) / 2 <= 528 pairs: up to three per thread)
   double* r2q = r2 + (long long)qi * m * m;
   const int npairs = m * (m + 1) / 2;
   constexpr int PP = (NNGP_MAX_NEIGHBOURS * (NNGP_MAX_NEIGHBOURS + 1) / 2 + PRO_THREADS - 1) / PRO_THREADS;
@@ -619,7 +771,7 @@ scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const 
     const int pidx = tid + u * PRO_THREADS;
     int a = 0, b = 0;
     if (pidx < npairs) {
-      a = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+      a = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
       while ((a + 1) * (a + 2) / 2 <= pidx) a++;
       while (a * (a + 1) / 2 > pidx) a--;
       b = pidx - a * (a + 1) / 2;
@@ -628,38 +780,19 @@ scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const 
     pb[u] = b;
     acc2[u] = 0.0;
   }
+  KNN_STAMP(6);
+#pragma unroll 1
   for (int j0 = 0; j0 < d; j0 += TILE_COLS) {
     const int jn = min(TILE_COLS, d - j0);
     __syncthreads();
-    {
-      double xv[4][8];
-#pragma unroll
-      for (int rr = 0; rr < 4; rr++) {
-        const int r = wid + rr * NW;
-        const double* xr = X + ((r < m) ? __ldcg(io + r) : 0) * d + j0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int c = lane + 32 * k;
-          xv[rr][k] = (r < m && c < jn) ? __ldg(xr + c) : 0.0;
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < 4; rr++) {
-        const int r = wid + rr * NW;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int c = lane + 32 * k;
-          if (r < m && c < jn) tile[r * TILE_LD + c] = xv[rr][k];
-        }
-      }
-    }
+    stage_rows<false, TILE_ROWS / NW>(X, io, 0, m, d, j0, jn, nullptr, tile, wid, lane);
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < PP; u++) {
       if (tid + u * PRO_THREADS < npairs) {
         const double *ta = tile + pa[u] * TILE_LD, *tb = tile + pb[u] * TILE_LD;
         double sacc = acc2[u];
-#pragma unroll 4
+#pragma unroll 16
         for (int c = 0; c < jn; c++) {
           const double diff = ta[c] - tb[c];
           sacc = sacc + diff * diff;
@@ -668,6 +801,7 @@ scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const 
       }
     }
   }
+  KNN_STAMP(7);
 #pragma unroll
   for (int u = 0; u < PP; u++) {
     if (tid + u * PRO_THREADS < npairs) {
@@ -676,6 +810,10 @@ scan_select_tile_kernel(const double* __restrict__ X, long long n, int d, const 
     }
   }
 }
+
+#ifdef NNGP_KNN_TIMING
+extern "C" void nngp_knn_stamps(long long* out) { cudaMemcpyFromSymbol(out, g_knn_stamps, sizeof(long long) * 16); }
+#endif
 
 // m > 32 (rare: nn='adaptive' past iteration 30): m passes of "smallest key above the last one" by one CTA per query
 __global__ void __launch_bounds__(256)
@@ -740,7 +878,7 @@ static constexpr int KNN_FUSED_MAX_Q = 4;  // queries per call served by scan_se
 size_t knn_workspace_bytes(int nq, long long n, int m) {
   const long long cr = knn_chunk_rows(nq, n);
   size_t chunks = (size_t)((n + cr - 1) / cr);
-  if (nq <= KNN_FUSED_MAX_Q) chunks = (size_t)((n + 31) / 32);  // TILE_ROWS of the small-dataset kernel (>= the 256-row chunks)
+  if (nq <= KNN_FUSED_MAX_Q) chunks = (size_t)((n + 15) / 16);  // SCAN_ROWS of the small-dataset kernel (>= the 256-row chunks)
   size_t b = knn_pad256(sizeof(double) * (size_t)nq * (size_t)n);
   if (chunks > 1 || nq <= KNN_FUSED_MAX_Q) b += 2 * knn_pad256(sizeof(double) * (size_t)nq * chunks * (size_t)m);
   return b;
@@ -755,7 +893,7 @@ static int scan_select_launch(nngp_handle_t h, const double* d_q, int nq, int m,
   static const bool no_tile = getenv("NNGP_KNN_NO_TILE") != nullptr;
   const size_t tile_smem = sizeof(double) * ((size_t)((d + 1) & ~1) + (size_t)TILE_ROWS * TILE_LD);
   if (n <= KNN_TILE_MAX_ROWS && !no_tile && tile_smem <= 200 * 1024) {
-    const unsigned tchunks = (unsigned)((n + TILE_ROWS - 1) / TILE_ROWS);
+    const unsigned tchunks = (unsigned)((n + SCAN_ROWS - 1) / SCAN_ROWS);
     double* tcand_d = (double*)base;
     long long* tcand_i = (long long*)(base + knn_pad256(sizeof(double) * (size_t)nq * tchunks * m));
     if (!h->attr_knn_tile) {
