@@ -479,7 +479,15 @@ def main():
                         "(20 of 32 lanes hold rows, full-row updates, 17-FMA exponentials): FP64 pipe 50 % busy in "
                         "profiles/r02/sweep_r2.summary.csv; 45 % of the evaluations are failing factorisations that "
                         "leave early (profiles/r02/fit_failing_pivots.log)"}
-    roof_rk = {"kernel": "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": R["rk_tf"], "peak": fp64_peak,
+    slices_rank = math.ceil(R["n_fine"] / world)
+    lone = slices_rank <= 148   # at most one slice per SM: the latency shape with shuffled halo columns (csrc/rk.cu)
+    quad_fit = world > 1 and (d // world) * 9 <= 3 * 148 * 3   # a rank's searches per predict <= the four-warp limit (csrc/gpfit.cu)
+    if quad_fit:
+        roof_fit["kernel"] = "gp_fit_spec_kernel<20> (four warps per search)"
+        roof_fit["executed_fp64_pipe_frac"] = None
+        roof_fit["executed_source"] = ("not captured for the four-warp kernel; the one-warp kernel on the same share: 20 % "
+                                       "(profiles/r02/fit_shard8_r2.summary.csv)")
+    roof_rk = {"kernel": "rk_fhn_tile_kernel<11,1,128,SHX>" if lone else "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": R["rk_tf"], "peak": fp64_peak,
                "unit": "TFLOP/s", "frac": R["rk_tf"] / fp64_peak if fp64_peak else None, "frac_of_nominal_37": R["rk_tf"] / 37.0,
                "traffic": 2158336, "traffic_source": "profiles/r01/rk_tile_r1.summary.csv (dram read+write bytes per launch)",
                "peak_source": peak_src,
@@ -491,8 +499,13 @@ def main():
                                       "tasks, 2 CTAs per SM (csrc/rk.cu launch_fhn_tile_s); algorithmic flops count the "
                                       "dense tableau as the reference evaluates it (SURVEY 8d), the kernel executes the 39+5 "
                                       "structural non-zeros: executed FP64 pipe utilisation 59 % (profiles/r01/rk_tile_r1.summary.csv)"},
-               "executed_fp64_pipe_frac": 0.59,
+               "executed_fp64_pipe_frac": 0.38 if lone else 0.59,
+               "executed_source": "profiles/r02/rk_lone_shuffle_r2.summary.csv" if lone else "profiles/r01/rk_tile_r1.summary.csv",
                "share_of_step": R["fine_ms"] / ms_step}
+    if lone:
+        roof_rk["per_launch"]["note"] = ("one launch, one CTA of 128 threads per slice (at most one slice per SM): bound by "
+                                         "the per-stage dependency chain, 235 cycles (DESIGN.md 4.1); algorithmic flops count "
+                                         "the dense tableau as the reference evaluates it (SURVEY 8d)")
     roofline, other = (roof_rk, roof_fit) if roof_rk["share_of_step"] >= roof_fit["share_of_step"] else (roof_fit, roof_rk)
     wl = workload_config(args)
     wl["iteration"] = args.iteration
