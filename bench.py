@@ -484,9 +484,10 @@ def main():
     quad_fit = world > 1 and (d // world) * 9 <= 3 * 148 * 3   # a rank's searches per predict <= the four-warp limit (csrc/gpfit.cu)
     if quad_fit:
         roof_fit["kernel"] = "gp_fit_spec_kernel<20> (four warps per search)"
-        roof_fit["executed_fp64_pipe_frac"] = None
-        roof_fit["executed_source"] = ("not captured for the four-warp kernel; the one-warp kernel on the same share: 20 % "
-                                       "(profiles/r02/fit_shard8_r2.summary.csv)")
+        roof_fit["executed_fp64_pipe_frac"] = 0.37
+        roof_fit["executed_source"] = ("profiles/r02/fit_quad8_r2.summary.csv (one rank's share of the 8-rank sweep: SM "
+                                       "sub-partitions active 55 % of the launch, 2.0x the instructions of the one-warp "
+                                       "kernel, which on the same share is active 25 % and at 20 %: fit_shard8_r2.summary.csv)")
     roof_rk = {"kernel": "rk_fhn_tile_kernel<11,1,128,SHX>" if lone else "rk_fhn_tile_kernel<11,2,64>", "bound": "fp64", "achieved": R["rk_tf"], "peak": fp64_peak,
                "unit": "TFLOP/s", "frac": R["rk_tf"] / fp64_peak if fp64_peak else None, "frac_of_nominal_37": R["rk_tf"] / 37.0,
                "traffic": 2158336, "traffic_source": "profiles/r01/rk_tile_r1.summary.csv (dram read+write bytes per launch)",
