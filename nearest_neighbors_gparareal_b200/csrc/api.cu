@@ -643,15 +643,30 @@ int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, lon
   signed char* gst = (signed char*)(dev + o_st);
   long long* gidx = (long long*)(dev + o_idx);
   double* gdist = (double*)(dev + o_dist);
-  NNGP_CUDA(h, cudaMemcpyAsync(gq, q, sizeof(double) * nqd, cudaMemcpyHostToDevice, st));
-  NNGP_CUDA(h, cudaMemcpyAsync(gst, starts, ntask * 2, cudaMemcpyHostToDevice, st));
   if (R < 1) return nngp_fail(h, "predict: n_restarts=%d < 1", R);
+  // query and starts are adjacent in the device block: one copy from the pinned staging buffer instead of two from
+  // pageable memory (a single predict of the sweep is latency-bound: every call on this path counts)
+  const size_t in_bytes = (o_st - o_q) + ntask * 2;
+  if (in_bytes <= (1u << 20)) {
+    char* pin = (char*)pinned_buf(h, in_bytes);
+    if (!pin) return nngp_fail(h, "predict_host: out of pinned memory");
+    memcpy(pin, q, sizeof(double) * nqd);
+    memcpy(pin + (o_st - o_q), starts, ntask * 2);
+    NNGP_CUDA(h, cudaMemcpyAsync(gq, pin, in_bytes, cudaMemcpyHostToDevice, st));
+  } else {
+    NNGP_CUDA(h, cudaMemcpyAsync(gq, q, sizeof(double) * nqd, cudaMemcpyHostToDevice, st));
+    NNGP_CUDA(h, cudaMemcpyAsync(gst, starts, ntask * 2, cudaMemcpyHostToDevice, st));
+  }
   void *kws, *fws;
   int* order;
   if (int rc = fit_workspace(h, nq, n, m, R, &kws, &fws, &order)) return rc;
   if (int rc = ensure_done_zero(h, fws, nq, d, m, R, st)) return rc;
-  if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
-  if (int rc = gp_prep_launch(h, gidx, nq, m, (double*)fws, st)) return rc;
+  if (nq == 1 && n >= m && knn_prep_fused_ok(h, n, m)) {  // the sweep's shape: scan + top-m + neighbour matrix in one launch
+    if (int rc = knn_prep_fused_launch(h, gq, m, n, gidx, gdist, (double*)fws, kws, h->d_ticket, st)) return rc;
+  } else {
+    if (int rc = knn_launch(h, gq, nq, m, n, gidx, gdist, kws, st)) return rc;
+    if (int rc = gp_prep_launch(h, gidx, nq, m, (double*)fws, st)) return rc;
+  }
   if (dl == d) {
     if (int rc = gp_order_launch(h, gst, nq, d * NNGP_N_JITTER * R, 1, order, st)) return rc;
   } else {  // the searches of the block are a contiguous range of the (single) query's task list
