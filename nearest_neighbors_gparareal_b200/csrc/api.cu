@@ -52,9 +52,19 @@ ProfScope::~ProfScope() {
 // (a fit uses up to three counters: its task queue, the number of parked long searches and their queue)
 static unsigned int* next_queue(nngp_handle_t h, cudaStream_t st) {
   if (h->queue_next + 4 > NNGP_QUEUE_SLOTS) {
+    // the bulk re-zeroing is ordered after the fits of `st` only: a fit still running on another stream of this
+    // handle (host entry points use the handle's own stream, device entry points the caller's) must finish first
+    if (h->queue_stream_valid && h->queue_stream != st) cudaStreamSynchronize(h->queue_stream);
     cudaMemsetAsync(h->d_queues, 0, NNGP_QUEUE_SLOTS * sizeof(unsigned int), st);
     h->queue_next = 0;
   }
+  if (h->queue_stream_valid && h->queue_stream != st && h->queue_next != 0) {
+    // the stream changed in the middle of a ring: the slots handed out so far may still be in use there, and a later
+    // wrap on either stream must not overtake them -- cheap (a stream switch is rare) and keeps the invariant simple
+    cudaStreamSynchronize(h->queue_stream);
+  }
+  h->queue_stream = st;
+  h->queue_stream_valid = true;
   unsigned int* p = h->d_queues + h->queue_next;
   h->queue_next += 4;
   return p;

@@ -76,6 +76,8 @@ struct nngp_handle_s {
   // is 1.4-4x faster; one search per warp for the serial sweep, whose searches fail early and cheaply 45 % of the
   // time -- DESIGN.md section 4.5), 1 always one search per warp, 2 always grouped.  NNGP_FIT_MODE=auto|warp|grouped
   int fit_mode = 0;
+  cudaStream_t queue_stream = nullptr;  // stream of the last fit that took a queue slot (next_queue)
+  bool queue_stream_valid = false;
   bool attr_knn_tile = false;  // scan_select_tile_kernel's shared-memory attribute set on this device
   // device counters: [0] Nelder-Mead runs, [1] objective (nll) evaluations
   unsigned long long* d_counters = nullptr;

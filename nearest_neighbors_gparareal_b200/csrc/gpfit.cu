@@ -12,7 +12,10 @@
 // independent warps pulls them with an atomic counter, so a warp that finishes a short search
 // immediately starts another one (search lengths vary from ~10 to 400 objective evaluations).  The
 // warp that completes the last search of an (query, dimension) pair applies the selection rule and
-// computes the posterior mean (no block barrier, no second launch).  Inside a warp the M(M-1)/2
+// computes the posterior mean (no block barrier, no second launch).  A launch with fewer searches than
+// warp slots (a rank's share of the dimension-sharded sweep) lasts as long as its longest search: there
+// gp_fit_spec_kernel gives a search the four warps of a CTA, which evaluate the points an iteration
+// can ask for side by side (same decisions, same bits).  Inside a warp the M(M-1)/2
 // kernel entries are spread over the lanes, exchanged through a per-warp shared-memory tile, and
 // lane r owns row r of the m x m kernel matrix (m <= 32) in registers: square-root-free
 // right-looking LDL^T, pivot broadcast by shuffle, column broadcast through the tile with

@@ -17,6 +17,9 @@
 // list spread over the lanes of a warp (lane l = l-th smallest), inserts a few survivors of a
 // round with ballot + shuffle and sorts / merges many with a bitonic network; warp 0 merges the
 // per-warp lists; few queries over many rows select in two levels (chunks, then candidates).
+// Small datasets with one to four queries (every predict of the sweep) take scan_select_tile_kernel further down:
+// 16-row tiles of the row-major copy staged through shared memory, integer images of the keys, and a level 2 that
+// ranks the few keys below the m-th smallest list head instead of sorting.
 #include "common.cuh"
 
 #include <cfloat>

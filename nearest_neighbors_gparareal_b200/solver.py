@@ -56,6 +56,11 @@ class SolverAbstr:
 
 
 class CudaSolverRK(SolverAbstr):
+    """solver.py:72-113 on the device.  h_mode: how the step sizes are formed -- 'linspace' = differences of
+    np.linspace(t0, t1, steps + 1) (RK.py:101-109 with use_jax=False, the path the golden fixtures were recorded
+    on, hence the default) or 'const' = (t1 - t0) / steps for every step (the jitted fori_loop of RK.py:146-203,
+    the reference's use_jax=True default).  The two differ in the last bits of h only."""
+
     def __init__(self, f, Ng, Nf, F, G, thresh=1e7, use_jax=True, h_mode='linspace', handle=None, **kwargs):
         if isinstance(f, ODE):
             f = f.get_vector_field()
