@@ -383,7 +383,12 @@ def test_prediction_given_identical_hyperparameters(handle, n, d, m):
 @pytest.mark.parametrize("n,d,m,R", [(300, 3, 11, 1), (600, 6, 15, 2), (800, 12, 20, 1), (300, 4, 30, 1)])
 def test_fit_predict_vs_oracle(handle, n, d, m, R):
     """full predict (kNN + 9R Nelder-Mead fits per dimension + selection + mean) against the oracle on
-    the same host-drawn starts"""
+    the same host-drawn starts.  A search leaves SciPy's trajectory at the first comparison of two objective values
+    that agree to the last ulp or two (the device's LDL^T objective and LAPACK's differ there; so do two LAPACK
+    builds): measured on the B200, 53-82 % of the searches follow it to the end (m = 20: 53 %, m = 11: 82 %) and the
+    selected optimum agrees to 1e-6 in 83-100 % of the dimensions.  The bars below sit just under those figures; what
+    is exact is asserted exactly (neighbours, the selection rule on the device's own values, the posterior mean at
+    the device's hyper-parameters)."""
     rng = np.random.default_rng(100 + m)
     x, y = make_dataset(rng, n, d)
     q = x[3] + 1e-3 * rng.standard_normal(d)
@@ -420,7 +425,9 @@ def test_fit_predict_vs_oracle(handle, n, d, m, R):
     # the selected optimum is as good as the reference's in (almost) every dimension: a search that
     # diverges from the SciPy trajectory at a last-bit tie may end in another local optimum
     close = np.abs(det['fval_opt'][0] - odet['fval_opt']) <= 1e-6 * np.maximum(1.0, np.abs(odet['fval_opt']))
-    assert close.mean() >= 0.75, (det['fval_opt'][0], odet['fval_opt'])
+    print(f"fit_predict n={n} d={d} m={m} R={R}: SciPy trajectory followed exactly by {frac:.3f} of the searches, "
+          f"selected optimum within 1e-6 in {close.mean():.3f} of the dimensions")
+    assert close.mean() >= 0.8, (det['fval_opt'][0], odet['fval_opt'])
     assert np.all(det['fval_opt'][0] <= odet['fval_opt'] + 0.2 * np.abs(odet['fval_opt']))
 
 
