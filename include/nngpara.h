@@ -130,7 +130,8 @@ int nngp_predict_host(nngp_handle_t h, const double* q, int nq, int m, long long
                       double* pred, long long* idx, double* theta_opt, double* jitter_opt,
                       double* fval_opt, int* nfev, double* fvals, double* thetas);
 /* One rank's share of a predict: the same, fits only for the output dimensions [j0, j0+dl) of a single query
- * (dl < 0: all); pred / theta_opt / ... are written for those dimensions only.                          */
+ * (dl < 0: all); pred / theta_opt / ... are written for those dimensions only.  `pred` may be a host or a device
+ * pointer (copied with cudaMemcpyDefault): ranks that all-gather their blocks keep it on the device.        */
 int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, long long n_rows,
                             int n_restarts, const signed char* starts, double fatol, double xatol, int j0, int dl,
                             double* pred, long long* idx, double* theta_opt, double* jitter_opt,

@@ -227,13 +227,14 @@ class Handle:
     def knn(self, d_q, nq, m, n_rows, d_idx, d_dist, stream=None):
         self.check(self.lib.nngp_knn(self.h, _ptr(d_q), int(nq), int(m), int(n_rows), _ptr(d_idx), _ptr(d_dist), stream))
 
-    def predict_host(self, q, m, starts, n_restarts, fatol, xatol, n_rows=0, details=False, block=None):
+    def predict_host(self, q, m, starts, n_restarts, fatol, xatol, n_rows=0, details=False, block=None, pred_out=None):
         q = as_f64(q)
         q = q.reshape(-1, q.shape[-1])
         nq, d = q.shape
         starts = np.ascontiguousarray(starts, dtype=np.int8)
         assert starts.size == nq * d * 9 * n_restarts * 2, "starts must be [nq,d,9,R,2]"
-        pred = np.empty((nq, d))
+        # pred_out: a caller-owned float64 buffer of nq*d values, host ndarray or device tensor (see nngpara.h)
+        pred = np.empty((nq, d)) if pred_out is None else pred_out
         out = dict(pred=pred)
         idx = th = jit = fv = nfev = fvals = thetas = None
         if details:

@@ -691,7 +691,9 @@ int nngp_predict_host_block(nngp_handle_t h, const double* q, int nq, int m, lon
                                      fvals ? (double*)(dev + o_fvals) : nullptr,
                                      thetas ? (double*)(dev + o_thetas) : nullptr, st, j0, dl))
     return rc;
-  NNGP_CUDA(h, cudaMemcpyAsync(pred, dev + o_pred, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));
+  // cudaMemcpyDefault: `pred` may be a host buffer or (unified addressing) a device buffer of the caller -- the ranks of a
+  // dimension-sharded host predict all-gather their blocks on the device and read the result back once
+  NNGP_CUDA(h, cudaMemcpyAsync(pred, dev + o_pred, sizeof(double) * nqd, cudaMemcpyDefault, st));
   if (idx) NNGP_CUDA(h, cudaMemcpyAsync(idx, gidx, sizeof(long long) * nq * m, cudaMemcpyDeviceToHost, st));
   if (theta_opt) NNGP_CUDA(h, cudaMemcpyAsync(theta_opt, dev + o_th, sizeof(double) * nqd * 2, cudaMemcpyDeviceToHost, st));
   if (jitter_opt) NNGP_CUDA(h, cudaMemcpyAsync(jitter_opt, dev + o_jit, sizeof(double) * nqd, cudaMemcpyDeviceToHost, st));

@@ -161,9 +161,16 @@ class CudaNNGP(ModelAbstr):
         starts = self.draw_starts(1)
         s = time.time()
         block = self._block()
+        dev_buf = self._device_gather_buffer() if block is not None else None
         out = h.predict_host(new_x, m, starts, self.n_restarts, self.fatol, self.xatol,
-                             details=details or self.collect_nfev, block=block)
-        if block is not None:
+                             details=details or self.collect_nfev, block=block, pred_out=dev_buf)
+        if dev_buf is not None:
+            # the rank's block is already on the device: all-gather in place, one read back
+            import torch.distributed as dist
+            j0, dl = block
+            dist.all_gather_into_tensor(dev_buf, dev_buf[j0:j0 + dl], group=self.group)
+            out['pred'] = dev_buf.cpu().numpy()[None, :]
+        elif block is not None:
             out['pred'] = self._gather(out['pred'], block)
         el = time.time() - s
         n_tasks = self.n * N_JITTER * self.n_restarts
@@ -189,6 +196,16 @@ class CudaNNGP(ModelAbstr):
         if world == 1 or self.n % world != 0:
             return None
         return dim_block(self.n, dist.get_rank(self.group), world)
+
+    def _device_gather_buffer(self):
+        """a d-double device tensor on the handle's GPU when the group's backend is NCCL (else None: host gather)"""
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(self.group) != 'nccl':
+            return None
+        if getattr(self, '_gather_buf', None) is None:
+            self._gather_buf = torch.empty(self.n, dtype=torch.float64, device=torch.device('cuda', self.handle().device))
+        return self._gather_buf
 
     def _gather(self, pred, block):
         """all-gather of the ranks' prediction blocks (d/W doubles each); details stay per-rank"""
