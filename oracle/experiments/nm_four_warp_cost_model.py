@@ -2,7 +2,8 @@
 per search (candidate points of an iteration evaluated side by side) on a replayed FHN d=512 predict: finite
 evaluation 3 300 cycles, failing evaluation 800, CTA barrier 150.  Strategies: A = {reflection, expansion, outside,
 inside contraction}; B = {reflection, inside contraction, both shrunk vertices}; C = B after an iteration that
-contracted inside or shrank (or when every vertex is +inf), else A  (= csrc/gpfit.cu gp_fit_spec_kernel).
+contracted inside or shrank (or when every vertex is +inf), else A  (= csrc/gpfit.cu gp_fit_spec_kernel);
+S6 = all six points an iteration can ask for (six warps per search: every iteration is one round).
 Result (profiles/r02/nm_moves.log): longest search 695 -> 336 us for 1.8x the evaluations (strategy C).
 usage: python oracle/experiments/nm_four_warp_cost_model.py [predict id = 3] [dimension stride = 8]"""
 import os, sys, collections, numpy as np
@@ -41,7 +42,8 @@ def run(func, x0, strategy, xatol=0.1, fatol=0.1):
             xbar = (sim[0] + sim[1]) / 2; worst = sim[2].copy()
             pts = {'xr': 2 * xbar - worst, 'xe': 3 * xbar - 2 * worst, 'xoc': 1.5 * xbar - 0.5 * worst,
                    'xic': 0.5 * xbar + 0.5 * worst, 's1': sim[0] + 0.5 * (sim[1] - sim[0]), 's2': sim[0] + 0.5 * (sim[2] - sim[0])}
-            if strategy == 'A': cand = ['xr', 'xe', 'xoc', 'xic']
+            if strategy == 'S6': cand = ['xr', 'xe', 'xoc', 'xic', 's1', 's2']
+            elif strategy == 'A': cand = ['xr', 'xe', 'xoc', 'xic']
             elif strategy == 'B': cand = ['xr', 'xic', 's1', 's2']
             else: cand = ['xr', 'xic', 's1', 's2'] if (last in ('IC', 'ICS', 'OCS', 'INF') or np.isinf(fsim[0])) else ['xr', 'xe', 'xoc', 'xic']
             used = []
@@ -78,7 +80,7 @@ step = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 xm, ym, starts = z[f'p{pid}_xm'], z[f'p{pid}_ym'], z[f'p{pid}_starts']
 r2 = onn.pairwise_sqdist(xm, xm)
 import warnings; warnings.filterwarnings('ignore')
-for strat in ('A', 'B', 'C'):
+for strat in (sys.argv[3].split(',') if len(sys.argv) > 3 else ('A', 'B', 'C')):
     S, Q, NF = [], [], []
     for j in range(0, 512, step):
         for a in range(9):
@@ -86,4 +88,4 @@ for strat in ('A', 'B', 'C'):
             s, q, n = run(f, starts[j, a, 0].astype(float), strat)
             S.append(s); Q.append(q); NF.append(n)
     S, Q = np.array(S), np.array(Q)
-    print(f'p{pid} strategy {strat}: serial max {S.max()/1.9e3:.0f} us mean {S.mean()/1.9e3:.0f} us | quad max {Q.max()/1.9e3:.0f} us mean {Q.mean()/1.9e3:.0f} us | sum ratio quad*4/serial {4*Q.sum()/S.sum():.2f}', flush=True)
+    print(f'p{pid} strategy {strat}: serial max {S.max()/1.9e3:.0f} us mean {S.mean()/1.9e3:.0f} us | quad max {Q.max()/1.9e3:.0f} us mean {Q.mean()/1.9e3:.0f} us | sum ratio warps*rounds/serial {(6 if strat == 'S6' else 4)*Q.sum()/S.sum():.2f}', flush=True)
