@@ -214,6 +214,7 @@ for d in (8, 6):
     pred[0, j0:j0 + dl] = np.arange(j0, j0 + dl) * 1.5 + 7      # this rank's share of the fits
     full = model._gather(pred, blk)
     ok &= bool(np.array_equal(full, (np.arange(d) * 1.5 + 7)[None, :]))
+    ok &= model._device_gather_buffer() is None               # gloo: the gather goes through host tensors
 model = CudaNNGP(n=7, N=4, nn=5, shard_predict=True)     # 7 % 2 != 0: not sharded
 ok &= model._block() is None
 ok &= CudaNNGP(n=8, N=4, nn=5)._block() is None           # sharding is opt-in
